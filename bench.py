@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched SGP4 `Satellite::propagate` on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2]
+
+A "step" is one pass of the hot path over one batch: every satellite of the rank's catalogue
+shard propagated to every time of the grid (BASELINE.json configs[1]: 30 000 near-Earth
+satellites x 1440 one-minute steps per GPU; weak scaling: the catalogue is N x 30 000
+satellites sharded by satellite range, no data-path collective).
+
+Prints ONE JSON line (rank 0). Keys beyond the base contract:
+  roofline      FP64-pipe roofline of kernel 2 (the binding one): algorithmic
+                flops per evaluation (flops-v0, frozen in F_ALG below) x evaluations per
+                launch / measured launch time, against a DFMA peak measured in this run.
+  roofline_hbm  the second roofline: 52 B written per evaluation against MEASURED_PEAKS.json.
+  cpu_baseline  the reference's scalar loop (oracle/_ref, else the C port) on the host cores.
+  e2e           the same metric through the C ABI with HOST buffers (H2D of the time grid and
+                D2H of all states and error codes inside the timed region).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# flops-v0 convention of SURVEY.md section 8d (frozen; change only together with that table)
+F_ALG = {0: 1170.0, 1: 1090.0, 2: 1502.0, 3: 1586.0, 4: 2097.0}
+BYTES_PER_EVAL = 52.0  # 48 B r,v + 4 B Sgp4Error written; reads amortise to < 1 B
+FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+
+WORKLOADS = {
+    # name: (synthetic config, satellites per GPU, times)
+    "c2": (2, 30000, 1440),
+    "c3": (3, 100000, 2000),
+    "c4": (4, 50000, 2016),
+    "c5": (5, 125000, 2000),
+}
+WORKLOAD_TEXT = {
+    "c2": "30k near-Earth synthetic LEO catalogue x 1440 one-minute steps per GPU",
+    "c3": "100k mixed near-Earth + deep-space catalogue x 2000 one-minute steps per GPU (time-chunk of the 10k grid)",
+    "c4": "50k GEO + Molniya resonant catalogue x 2016 steps per GPU (chunk of the 7-day grid)",
+    "c5": "1M mega-constellation / 8 = 125k satellites x 2000 steps per GPU (chunk of the 10k grid)",
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.power = []
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+            "power_w_max": max(self.power) if self.power else None,
+        }
+
+
+def catalogue_lines(workload, rank, world):
+    """Global catalogue of world x n satellites, this rank's satellite range."""
+    import perturb_b200 as pb
+    cfg, n, m = WORKLOADS[workload]
+    total = n * world
+    b1, b2 = pb.synth_catalog(cfg, total)
+    s = pb.capi.SYNTH_LINE_STRIDE
+    lo, hi = rank * n, (rank + 1) * n
+    return b1[lo * s: hi * s], b2[lo * s: hi * s], n, m
+
+
+def cpu_arm(workload, steps, warmup, cores=None, budget_s=12.0):
+    """The reference's scalar loop on all host cores over a bounded sample of the workload."""
+    import perturb_b200 as pb
+    from oracle import port, ref
+    cfg, n, m = WORKLOADS[workload]
+    b1, b2, n, m = catalogue_lines(workload, 0, 1)
+    cores = cores or (os.cpu_count() or 1)
+    jd, fr = pb.synth_time_grid(m)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    use_ref = ref.available()
+
+    def make(k):
+        if use_ref:
+            return ref.RefSatellites.from_tle_lines(L1[:k], L2[:k])
+        return port.OracleSatellites.from_tle_lines(L1[:k], L2[:k], 1, "i", flavor=1)
+
+    probe_n = min(n, 64 * cores)
+    sats = make(probe_n)
+    _, _, _, secs = sats.propagate_grid(jd, fr, use_jd=True, nthreads=cores, want_state=False)
+    rate = probe_n * m / max(secs, 1e-9)
+    k = int(min(n, max(probe_n, rate * budget_s / max(1, steps + warmup) / m)))
+    sats = make(k)
+    times = []
+    for it in range(warmup + steps):
+        _, _, _, secs = sats.propagate_grid(jd, fr, use_jd=True, nthreads=cores, want_state=True)
+        if it >= warmup:
+            times.append(secs)
+    value = k * m * len(times) / sum(times)
+    return {
+        "value": value,
+        "unit": "evals/s",
+        "cores": cores,
+        "kind": "reference" if use_ref else "port",
+        "sample": "%d of %d satellites x all %d times per step, %d steps (walked in time order, "
+                  "one contiguous satellite slice per thread)" % (k, n, m, len(times)),
+        "ms_per_step": 1e3 * sum(times) / len(times),
+        "sample_evals": k * m,
+    }
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    base = cpu_arm(args.workload, args.steps, args.warmup, budget_s=60.0)
+    cfg, n, m = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference",
+        "metric": "SGP4 evals/sec (sat x time)",
+        "value": base["value"],
+        "unit": "evals/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "satellites_per_gpu": n, "times": m},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    import perturb_b200 as pb
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    b1, b2, n, m = catalogue_lines(args.workload, rank, world)
+    t0 = time.perf_counter()
+    tles, status = pb.parse_tle_blocks(b1, b2, n, flavor=1)
+    t_parse = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    batch = pb.SatelliteBatch.from_parsed(tles, pb.WGS72, "i", device=local)
+    t_init = time.perf_counter() - t0
+    cls = np.bincount(batch.orbit_class(), minlength=5)
+    falg = float(sum(F_ALG[c] * cls[c] for c in range(5)) / max(1, cls.sum()))
+
+    jd, fr = pb.synth_time_grid(m)
+    d_jd = torch.tensor(jd, device=dev)
+    d_fr = torch.tensor(fr, device=dev)
+    out = torch.empty((6, n, m), dtype=torch.float64, device=dev)
+    err = torch.empty((n, m), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    peak = pb.capi.C.c_double(0.0)
+    pb.capi.check(pb.capi.lib().perturb_gpu_measure_fp64_peak(local, pb.capi.C.byref(peak)),
+                  "perturb_gpu_measure_fp64_peak")
+    fp64_peak = peak.value
+
+    def step():
+        batch.propagate(d_jd, d_fr, out, err, stream=sp, sync=False)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    launches_per_step = batch.last_launch_count()
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    # keep the GPU under the same load a little longer if the region was too short to sample
+    while len(sampler.samples) < 5 and time.perf_counter() - wall0 < 3.0:
+        step()
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    if dist is not None:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    evals_step_rank = float(n) * m
+    value = evals_step_rank * world * args.steps / (max_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers ----
+    h_jd = torch.tensor(jd).pin_memory()
+    h_fr = torch.tensor(fr).pin_memory()
+    h_out = torch.empty((6, n, m), dtype=torch.float64).pin_memory()
+    h_err = torch.empty((n, m), dtype=torch.int32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    batch.propagate(h_jd, h_fr, h_out, h_err)  # warm-up: allocates the staging buffers
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.propagate(h_jd, h_fr, h_out, h_err)  # synchronises: results are on the host
+        _ = int(h_err[0, 0])
+    e2e_s = time.perf_counter() - te
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = evals_step_rank * world * e2e_steps / float(t.item())
+    codes_ok = float((h_err == 0).double().mean())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = max_ms / args.steps
+    launch_ms = total_ms / args.steps  # rank 0's own average launch group
+    achieved_tflops = falg * evals_step_rank / (launch_ms * 1e-3) * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+            args.workload)
+    except Exception:
+        pass
+    cpu = cpu_arm(args.workload, 2, 1) if world == 1 or rank == 0 else None
+    line = {
+        "metric": "SGP4 evals/sec (sat x time)",
+        "value": value,
+        "unit": "evals/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD_TEXT[args.workload],
+            "satellites_per_gpu": n, "times": m, "evals_per_step": evals_step_rank * world,
+            "orbit_classes": {"near_full": int(cls[0]), "near_simplified": int(cls[1]),
+                              "deep_nonresonant": int(cls[2]), "deep_24h": int(cls[3]),
+                              "deep_12h": int(cls[4])},
+            "sharding": "satellite ranges, one process per GPU, no data-path collective",
+            "l2": "256 MiB buffer rewritten between timed iterations (outside the event pair); "
+                  "each step also writes %.2f GB of outputs" % (evals_step_rank * 52 / 1e9),
+            "outputs": "device-resident SoA planes [6][n][m] f64 + err [n][m] i32",
+        },
+        "roofline": {
+            "bound": "fp64",
+            "achieved": achieved_tflops,
+            "peak": fp64_peak,
+            "unit": "TFLOP/s",
+            "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None,
+            "traffic": traffic,
+            "peak_source": "DFMA microbenchmark measured in this run (perturb_gpu_measure_fp64_peak)",
+            "peak_nominal": FP64_NOMINAL_TFLOPS,
+            "frac_of_nominal": achieved_tflops / FP64_NOMINAL_TFLOPS,
+            "flops_per_eval": falg,
+            "kernel": "sgp4_prop_kernel (all class launches of one step)",
+            "launch_ms": launch_ms,
+        },
+        "roofline_hbm": {
+            "bound": "hbm",
+            "achieved": BYTES_PER_EVAL * evals_step_rank / (launch_ms * 1e-3) * 1e-9,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": BYTES_PER_EVAL * evals_step_rank / (launch_ms * 1e-3) * 1e-9 / hbm_peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+        },
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {
+            "value": e2e_value,
+            "unit": "evals/s",
+            "h2d_bytes_per_step": int(2 * m * 8),
+            "d2h_bytes_per_step": int(evals_step_rank * 52),
+            "steps": e2e_steps,
+            "host_buffers": "pinned",
+        },
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks,
+        "init": {"satellites": n, "parse_ms": 1e3 * t_parse, "sgp4init_and_sort_ms": 1e3 * t_init},
+        "wall_s_timed_region": wall,
+        "ok_fraction": codes_ok,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+/*
+ * perturb_gpu.h -- C ABI of the B200 batched SGP4/SDP4 propagator.
+ *
+ * Drop-in boundary for ONE path of gunvirranu/perturb: a loop over
+ *     Sgp4Error Satellite::propagate(JulianDate, StateVector&)          src/perturb.cpp:236-242
+ *     Sgp4Error Satellite::propagate_from_epoch(double, StateVector&)   src/perturb.cpp:228-234
+ * on satellites built by
+ *     Satellite::Satellite(const TwoLineElement&, GravModel)            src/perturb.cpp:135-186
+ *     Satellite::from_tle(char*, char*, GravModel)                      src/perturb.cpp:189-205
+ * The reference has no FFI layer of its own; these entry points are what a binding for that
+ * path would bind (INTEGRATION.md shows the C++ shim a maintainer adds to perturb).
+ *
+ * Conventions kept from the reference (include/perturb/perturb.hpp:37-60, README.md:19-20):
+ *   - nothing throws; every call returns a status. Library status (this header) is separate
+ *     from the per-satellite / per-evaluation `Sgp4Error` codes, which are DATA;
+ *   - the caller owns every input and output buffer; the library owns only the handle;
+ *   - a handle is not re-entrant (like a `Satellite`); distinct handles are independent;
+ *   - position [km] / velocity [km/s] in TEME are written for codes NONE(0) and DECAYED(6)
+ *     only; for codes 1-4 the reference leaves the caller's StateVector untouched
+ *     (src/sgp4.cpp:1865,1878,1943,1995) -- the batch writes quiet NaNs there.
+ *
+ * Buffers may be host or device pointers (detected with cudaPointerGetAttributes). Device
+ * outputs are written directly by the kernel; host outputs go through a device staging
+ * buffer owned by the handle and an asynchronous D2H copy (pinned host memory recommended).
+ * There is no CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef PERTURB_GPU_H
+#define PERTURB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library status codes (negative = failure). Never an Sgp4Error. */
+enum {
+    PERTURB_GPU_OK = 0,
+    PERTURB_GPU_ERR_ARG = -1,    /* null / inconsistent arguments                      */
+    PERTURB_GPU_ERR_CUDA = -2,   /* a CUDA runtime call failed; see perturb_gpu_strerror */
+    PERTURB_GPU_ERR_NODEV = -3,  /* no usable CUDA device                              */
+    PERTURB_GPU_ERR_ALLOC = -4   /* host or device allocation failed                   */
+};
+
+/* perturb::GravModel, include/perturb/perturb.hpp:69-73 (same order). */
+enum { PERTURB_GPU_WGS72_OLD = 0, PERTURB_GPU_WGS72 = 1, PERTURB_GPU_WGS84 = 2 };
+
+/* perturb::Sgp4Error, include/perturb/perturb.hpp:50-60 (same values). */
+enum {
+    PERTURB_SGP4_NONE = 0,
+    PERTURB_SGP4_MEAN_ELEMENTS = 1,
+    PERTURB_SGP4_MEAN_MOTION = 2,
+    PERTURB_SGP4_PERT_ELEMENTS = 3,
+    PERTURB_SGP4_SEMI_LATUS_RECTUM = 4,
+    PERTURB_SGP4_EPOCH_ELEMENTS_SUB_ORBITAL = 5,
+    PERTURB_SGP4_DECAYED = 6,
+    PERTURB_SGP4_INVALID_TLE = 7,
+    PERTURB_SGP4_UNKNOWN = 8
+};
+
+/* Numeric members of perturb::TwoLineElement (include/perturb/tle.hpp:65-91), TLE units:
+ * degrees, rev/day, two-digit epoch year + fractional day of year. Members the propagator
+ * never reads (catalog number, designator, checksums ...) are not carried.
+ * An entry whose epoch_year or mean_motion is NaN stands for a TLE the parser rejected: its
+ * record is zeroed, its init error is INVALID_TLE and it propagates to MEAN_MOTION(2), which
+ * is what the reference does with such a `Satellite` (src/perturb.cpp:190-196). */
+typedef struct perturb_gpu_tle {
+    double epoch_year;
+    double epoch_day_of_year;
+    double n_dot;
+    double n_ddot;
+    double b_star;
+    double inclination;
+    double raan;
+    double eccentricity;
+    double arg_of_perigee;
+    double mean_anomaly;
+    double mean_motion;
+} perturb_gpu_tle;
+
+typedef struct perturb_gpu_batch perturb_gpu_batch; /* opaque */
+
+/* ---- construction -------------------------------------------------------------------- */
+
+/* Replaces n x `Satellite(const TwoLineElement&, GravModel)` (src/perturb.cpp:135-186),
+ * i.e. unit conversion + epoch + sgp4::sgp4init (src/sgp4.cpp:1383-1680) in kernel 1, then
+ * classifies (near/deep, isimp, irez) and sorts the batch for kernel 2.
+ *   tles       [n] host or device
+ *   grav_model PERTURB_GPU_WGS72 is the reference default
+ *   opsmode    'i' (what the reference's public API hard-wires, perturb.cpp:182,200) or 'a'
+ *              (what its verification test uses, tests/test_perturb.cpp:35)
+ *   device     CUDA device ordinal
+ *   init_error [n] host, may be NULL: `Satellite::last_error()` after construction, caller order
+ */
+int perturb_gpu_init(const perturb_gpu_tle *tles, size_t n, int grav_model, char opsmode,
+                     int device, perturb_gpu_batch **out, int32_t *init_error);
+
+/* Alternate entry: satellites whose `sgp4::elsetrec` was initialised elsewhere (replaces
+ * n x `Satellite(sgp4::elsetrec)`, src/perturb.cpp:133). `records` is field-major
+ * [perturb_gpu_record_field_count()][n] doubles (host or device), field order given by
+ * perturb_gpu_record_field_name(). Kernel 1 is skipped; this isolates kernel 2. */
+int perturb_gpu_init_records(const double *records, size_t n, int grav_model, char opsmode,
+                             int device, perturb_gpu_batch **out, int32_t *init_error);
+
+void perturb_gpu_free(perturb_gpu_batch *batch);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* Replaces, for every satellite i < n and every time k < m,
+ *     err = sats[i].propagate(JulianDate(jd[k], jd_frac[k]), sv)        perturb.cpp:236-242
+ * Outputs (host or device, caller-owned, satellites in CALLER order):
+ *   posvel  six planes x, y, z [km], vx, vy, vz [km/s]:
+ *             posvel[c * plane_stride + i * row_stride + k]       (strides in doubles)
+ *   err     err[i * row_stride + k], Sgp4Error values
+ * row_stride >= m lets a caller fill a wider [n][M] matrix one time-chunk at a time;
+ * plane_stride >= n * row_stride. `stream` is a cudaStream_t (NULL = default stream). The
+ * call returns after enqueueing when all buffers are device or pinned-host memory; use
+ * perturb_gpu_synchronize() before reading host outputs. */
+int perturb_gpu_propagate(perturb_gpu_batch *batch, const double *jd, const double *jd_frac,
+                          size_t m, double *posvel, int32_t *err, size_t row_stride,
+                          size_t plane_stride, void *stream);
+
+/* Same for `propagate_from_epoch(mins[k], sv)` (perturb.cpp:228-234). */
+int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *mins, size_t m,
+                                     double *posvel, int32_t *err, size_t row_stride,
+                                     size_t plane_stride, void *stream);
+
+int perturb_gpu_synchronize(perturb_gpu_batch *batch);
+
+/* ---- queries ------------------------------------------------------------------------- */
+
+size_t perturb_gpu_size(const perturb_gpu_batch *batch);
+int perturb_gpu_device(const perturb_gpu_batch *batch);
+
+/* `Satellite::last_error()` right after construction, caller order; out [n] host. */
+int perturb_gpu_last_error(const perturb_gpu_batch *batch, int32_t *out);
+
+/* `Satellite::epoch()` (perturb.cpp:224-226); out arrays [n] host. */
+int perturb_gpu_epoch(const perturb_gpu_batch *batch, double *jd, double *jd_frac);
+
+/* Orbit class per satellite (0 near full drag, 1 near simplified, 2 deep non-resonant,
+ * 3 deep 24 h resonant, 4 deep 12 h resonant); out [n] host. */
+int perturb_gpu_orbit_class(const perturb_gpu_batch *batch, uint8_t *out);
+
+/* The device-resident mirror of `Satellite::sat_rec` (sgp4::elsetrec numerics). */
+int perturb_gpu_record_field_count(void);
+const char *perturb_gpu_record_field_name(int field);
+/* out [n] host, caller order. */
+int perturb_gpu_record_field(const perturb_gpu_batch *batch, int field, double *out);
+
+/* Number of kernel launches the last propagate call on this handle issued. */
+int perturb_gpu_last_launch_count(const perturb_gpu_batch *batch);
+
+/* FP64 roofline denominator: DFMA-only microbenchmark on `device` (no memory traffic),
+ * best of 5 after a warm-up; *tflops counts a DFMA as 2 flops. Used by bench.py. */
+int perturb_gpu_measure_fp64_peak(int device, double *tflops);
+
+/* Message for the most recent failure on the calling thread. */
+const char *perturb_gpu_strerror(void);
+
+/* ---- host-side TLE text front end ------------------------------------------------------ */
+
+/* Fixed-column reader for n TLEs. lines1/lines2 hold n records of `line_stride` bytes each
+ * (>= 69 used; no terminator needed). flavor 0 follows TwoLineElement::parse's numeric
+ * conventions (src/tle.cpp:123-138), flavor 1 follows twoline2rv's (src/sgp4.cpp:2231-2338);
+ * they differ in the last bit of n_ddot / b_star only. status [n] may be NULL: 0 ok, else a
+ * perturb::TLEParseError value (include/perturb/tle.hpp:45-51); rejected entries are set to
+ * NaN so that perturb_gpu_init() reports INVALID_TLE for them. */
+int perturb_gpu_parse_tles(const char *lines1, const char *lines2, size_t line_stride, size_t n,
+                           int flavor, perturb_gpu_tle *out, int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERTURB_GPU_H */

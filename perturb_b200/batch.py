@@ -1,0 +1,226 @@
+"""Python mirror of `perturb::SatelliteBatch` (include/perturb/satellite_batch.hpp).
+
+Same names and argument meaning as the reference's `Satellite` interface for this path
+(include/perturb/perturb.hpp:241-322), batched:
+
+    Satellite::from_tle(line_1, line_2, grav)     -> SatelliteBatch.from_tles(lines1, lines2, grav)
+    Satellite(const TwoLineElement&, grav)        -> SatelliteBatch.from_parsed(tles, grav)
+    Satellite(sgp4::elsetrec)                     -> SatelliteBatch.from_records(records, grav)
+    sat.last_error()                              -> batch.last_error()          [n]
+    sat.epoch()                                   -> batch.epoch()               ([n], [n])
+    sat.propagate(JulianDate, sv)                 -> batch.propagate(jd, jd_frac)
+    sat.propagate_from_epoch(mins, sv)            -> batch.propagate_from_epoch(mins)
+
+Everything goes through the C ABI (perturb_b200/capi.py); torch is used only to own device /
+pinned buffers. Never raises on per-satellite problems: those are Sgp4Error codes in the
+returned arrays, like the reference.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _as_line_block(lines, stride=capi.SYNTH_LINE_STRIDE):
+    """list[str] -> one bytes block of fixed-stride records (NUL padded)."""
+    buf = bytearray(len(lines) * stride)
+    for i, ln in enumerate(lines):
+        b = ln.encode("ascii", "replace")[: stride - 1]
+        buf[i * stride: i * stride + len(b)] = b
+    return bytes(buf)
+
+
+def parse_tles(lines1, lines2, flavor=1):
+    """Host TLE text front end. Returns (ctypes Tle array, status[n]).
+
+    flavor 1 = numeric conventions of `Satellite::from_tle` / twoline2rv,
+    flavor 0 = those of `TwoLineElement::parse`."""
+    n = len(lines1)
+    if isinstance(lines1, (bytes, bytearray)):
+        raise TypeError("pass lists of strings, or use parse_tle_blocks for raw blocks")
+    return parse_tle_blocks(_as_line_block(lines1), _as_line_block(lines2), n, flavor)
+
+
+def parse_tle_blocks(block1, block2, n, flavor=1, stride=capi.SYNTH_LINE_STRIDE):
+    out = (capi.Tle * n)()
+    status = np.zeros(n, dtype=np.int32)
+    st = capi.lib().perturb_gpu_parse_tles(
+        block1, block2, stride, n, flavor, out, status.ctypes.data_as(C.POINTER(C.c_int32)))
+    capi.check(st, "perturb_gpu_parse_tles")
+    return out, status
+
+
+def synth_catalog(config, n, seed=0):
+    """Synthetic catalogue of BASELINE config `config` as two fixed-stride line blocks."""
+    b1 = C.create_string_buffer(n * capi.SYNTH_LINE_STRIDE)
+    b2 = C.create_string_buffer(n * capi.SYNTH_LINE_STRIDE)
+    st = capi.lib().perturb_synth_catalog(config, n, seed, b1, b2)
+    if st != 0:
+        raise ValueError("bad synthetic catalogue arguments")
+    return b1.raw, b2.raw
+
+
+def block_to_lines(block, n, stride=capi.SYNTH_LINE_STRIDE):
+    return [block[i * stride: i * stride + 69].decode("ascii") for i in range(n)]
+
+
+def synth_time_grid(m):
+    jd = np.zeros(m)
+    fr = np.zeros(m)
+    dp = C.POINTER(C.c_double)
+    capi.lib().perturb_synth_time_grid(m, jd.ctypes.data_as(dp), fr.ctypes.data_as(dp))
+    return jd, fr
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+class SatelliteBatch:
+    def __init__(self, handle, n):
+        self._h = handle
+        self.n = n
+
+    # ---- construction -----------------------------------------------------------------
+    @classmethod
+    def _create(cls, fn, src, n, grav, opsmode, device):
+        h = C.c_void_p()
+        init_error = np.zeros(n, dtype=np.int32)
+        st = fn(src, n, int(grav), opsmode.encode(), int(device), C.byref(h),
+                init_error.ctypes.data_as(C.POINTER(C.c_int32)))
+        capi.check(st, fn.__name__)
+        self = cls(h, n)
+        self._init_error = init_error
+        return self
+
+    @classmethod
+    def from_parsed(cls, tles, grav=capi.WGS72, opsmode="i", device=0):
+        """`tles`: ctypes array of capi.Tle (TLE units), or float64 array [n, 11]."""
+        if isinstance(tles, np.ndarray):
+            arr = np.ascontiguousarray(tles, dtype=np.float64)
+            assert arr.ndim == 2 and arr.shape[1] == len(capi.TLE_FIELDS)
+            n, src = arr.shape[0], arr.ctypes.data
+            self = cls._create(capi.lib().perturb_gpu_init, src, n, grav, opsmode, device)
+            return self
+        n = len(tles)
+        return cls._create(capi.lib().perturb_gpu_init, C.addressof(tles) if n else None, n,
+                           grav, opsmode, device)
+
+    @classmethod
+    def from_tles(cls, lines1, lines2, grav=capi.WGS72, opsmode="i", device=0, flavor=1):
+        tles, status = parse_tles(lines1, lines2, flavor)
+        self = cls.from_parsed(tles, grav, opsmode, device)
+        self.parse_status = status
+        return self
+
+    @classmethod
+    def from_records(cls, records, grav=capi.WGS72, opsmode="i", device=0):
+        """records: float64 [record_field_count, n], field order = record_field_names()."""
+        arr = np.ascontiguousarray(records, dtype=np.float64)
+        assert arr.ndim == 2 and arr.shape[0] == capi.lib().perturb_gpu_record_field_count()
+        return cls._create(capi.lib().perturb_gpu_init_records, arr.ctypes.data, arr.shape[1],
+                           grav, opsmode, device)
+
+    def close(self):
+        if self._h:
+            capi.lib().perturb_gpu_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- queries ----------------------------------------------------------------------
+    def last_error(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        capi.check(capi.lib().perturb_gpu_last_error(
+            self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), "perturb_gpu_last_error")
+        return out
+
+    def epoch(self):
+        jd = np.zeros(self.n)
+        fr = np.zeros(self.n)
+        dp = C.POINTER(C.c_double)
+        capi.check(capi.lib().perturb_gpu_epoch(
+            self._h, jd.ctypes.data_as(dp), fr.ctypes.data_as(dp)), "perturb_gpu_epoch")
+        return jd, fr
+
+    def orbit_class(self):
+        out = np.zeros(self.n, dtype=np.uint8)
+        capi.check(capi.lib().perturb_gpu_orbit_class(
+            self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))), "perturb_gpu_orbit_class")
+        return out
+
+    @staticmethod
+    def record_field_names():
+        L = capi.lib()
+        return [L.perturb_gpu_record_field_name(i).decode()
+                for i in range(L.perturb_gpu_record_field_count())]
+
+    def record_field(self, name):
+        idx = self.record_field_names().index(name)
+        out = np.zeros(self.n)
+        capi.check(capi.lib().perturb_gpu_record_field(
+            self._h, idx, out.ctypes.data_as(C.POINTER(C.c_double))), "perturb_gpu_record_field")
+        return out
+
+    def records(self):
+        return np.stack([self.record_field(nm) for nm in self.record_field_names()])
+
+    def last_launch_count(self):
+        return capi.lib().perturb_gpu_last_launch_count(self._h)
+
+    def synchronize(self):
+        capi.check(capi.lib().perturb_gpu_synchronize(self._h), "perturb_gpu_synchronize")
+
+    # ---- the hot path -----------------------------------------------------------------
+    def _outputs(self, m, posvel, err):
+        if posvel is None:
+            posvel = np.empty((6, self.n, m), dtype=np.float64)
+        if err is None:
+            err = np.empty((self.n, m), dtype=np.int32)
+        return posvel, err
+
+    @staticmethod
+    def _strides(posvel, n, m):
+        if isinstance(posvel, np.ndarray):
+            es = posvel.itemsize
+            s = [x // es for x in posvel.strides]
+        else:
+            s = list(posvel.stride())
+        assert s[2] == 1, "time must be the contiguous axis"
+        return s[1], s[0]  # row_stride, plane_stride (doubles)
+
+    def propagate(self, jd, jd_frac, posvel=None, err=None, stream=None, sync=True):
+        """All satellites x all JulianDate(jd[k], jd_frac[k]).
+
+        Returns (posvel [6, n, m] = x,y,z [km], vx,vy,vz [km/s]; err [n, m] Sgp4Error).
+        jd/jd_frac/posvel/err may be numpy arrays (host) or torch CUDA tensors (device)."""
+        m = int(jd.shape[0])
+        posvel, err = self._outputs(m, posvel, err)
+        row, plane = self._strides(posvel, self.n, m)
+        st = capi.lib().perturb_gpu_propagate(
+            self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(posvel), _ptr(err), row, plane, stream)
+        capi.check(st, "perturb_gpu_propagate")
+        if sync:
+            self.synchronize()
+        return posvel, err
+
+    def propagate_from_epoch(self, mins, posvel=None, err=None, stream=None, sync=True):
+        m = int(mins.shape[0])
+        posvel, err = self._outputs(m, posvel, err)
+        row, plane = self._strides(posvel, self.n, m)
+        st = capi.lib().perturb_gpu_propagate_from_epoch(
+            self._h, _ptr(mins), m, _ptr(posvel), _ptr(err), row, plane, stream)
+        capi.check(st, "perturb_gpu_propagate_from_epoch")
+        if sync:
+            self.synchronize()
+        return posvel, err

@@ -1,0 +1,90 @@
+"""ctypes view of the C ABI in include/perturb_gpu.h and include/perturb_synth.h.
+
+The shared library is built in-tree (perturb_b200/libperturb_gpu.so, see csrc/Makefile).
+There is no CPU fallback: if the library is missing, loading fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libperturb_gpu.so")
+
+OK = 0
+WGS72_OLD, WGS72, WGS84 = 0, 1, 2
+SYNTH_LEO, SYNTH_MIXED, SYNTH_DEEP, SYNTH_MEGA = 2, 3, 4, 5
+SYNTH_LINE_STRIDE = 70
+
+TLE_FIELDS = (
+    "epoch_year epoch_day_of_year n_dot n_ddot b_star inclination raan eccentricity "
+    "arg_of_perigee mean_anomaly mean_motion"
+).split()
+
+
+class Tle(C.Structure):
+    """perturb_gpu_tle: numeric members of perturb::TwoLineElement (tle.hpp:65-91)."""
+    _fields_ = [(n, C.c_double) for n in TLE_FIELDS]
+
+
+# Every symbol include/perturb_gpu.h and include/perturb_synth.h declare.
+EXPORTS = (
+    "perturb_gpu_init perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
+    "perturb_gpu_propagate_from_epoch perturb_gpu_synchronize perturb_gpu_size "
+    "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
+    "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
+    "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles "
+    "perturb_gpu_measure_fp64_peak "
+    "perturb_synth_catalog perturb_synth_time_grid"
+).split()
+
+_lib = None
+
+
+class PerturbGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PerturbGpuError(
+            "%s is missing: build it with `make -C perturb_b200/csrc` (or "
+            "__graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.perturb_gpu_init.argtypes = [
+        vp, C.c_size_t, C.c_int, C.c_char, C.c_int, C.POINTER(vp), ip]
+    L.perturb_gpu_init_records.argtypes = L.perturb_gpu_init.argtypes
+    L.perturb_gpu_free.argtypes = [vp]
+    L.perturb_gpu_free.restype = None
+    L.perturb_gpu_propagate.argtypes = [
+        vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_size_t, vp]
+    L.perturb_gpu_propagate_from_epoch.argtypes = [
+        vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_size_t, vp]
+    L.perturb_gpu_synchronize.argtypes = [vp]
+    L.perturb_gpu_size.argtypes = [vp]
+    L.perturb_gpu_size.restype = C.c_size_t
+    L.perturb_gpu_device.argtypes = [vp]
+    L.perturb_gpu_last_error.argtypes = [vp, ip]
+    L.perturb_gpu_epoch.argtypes = [vp, dp, dp]
+    L.perturb_gpu_orbit_class.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.perturb_gpu_record_field_name.argtypes = [C.c_int]
+    L.perturb_gpu_record_field_name.restype = C.c_char_p
+    L.perturb_gpu_record_field.argtypes = [vp, C.c_int, dp]
+    L.perturb_gpu_last_launch_count.argtypes = [vp]
+    L.perturb_gpu_strerror.restype = C.c_char_p
+    L.perturb_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    L.perturb_gpu_parse_tles.argtypes = [
+        C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Tle), ip]
+    L.perturb_synth_catalog.argtypes = [
+        C.c_int, C.c_size_t, C.c_uint64, C.c_char_p, C.c_char_p]
+    L.perturb_synth_time_grid.argtypes = [C.c_size_t, dp, dp]
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != OK:
+        msg = lib().perturb_gpu_strerror()
+        raise PerturbGpuError("%s failed (%d): %s" % (what, status, (msg or b"").decode()))

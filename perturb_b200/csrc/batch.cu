@@ -1,0 +1,553 @@
+// Host side of the C ABI (include/perturb_gpu.h): handle management, classification + sort,
+// launches, host<->device staging. C++11, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/perturb_gpu.h"
+#include "batch_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+int fail(int status, const std::string &msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define PB_CUDA(call)                                                                        \
+    do {                                                                                     \
+        const cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                             \
+            return fail(PERTURB_GPU_ERR_CUDA,                                                \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+        }                                                                                    \
+    } while (0)
+
+const char *const kRecordFieldNames[RF_COUNT] = {
+#define X(name) #name,
+    PB_RECORD_FIELDS(X)
+#undef X
+};
+
+bool is_device_pointer(const void *p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// getgravconst, src/sgp4.cpp:2101-2157
+bool gravity_constants(int model, pb::GravAll &g) {
+    switch (model) {
+        case PERTURB_GPU_WGS72_OLD:
+            g.mus = 398600.79964;
+            g.radiusearthkm = 6378.135;
+            g.xke = 0.0743669161;
+            g.j2 = 0.001082616;
+            g.j3 = -0.00000253881;
+            g.j4 = -0.00000165597;
+            break;
+        case PERTURB_GPU_WGS72:
+            g.mus = 398600.8;
+            g.radiusearthkm = 6378.135;
+            g.xke = 60.0 / std::sqrt(g.radiusearthkm * g.radiusearthkm * g.radiusearthkm / g.mus);
+            g.j2 = 0.001082616;
+            g.j3 = -0.00000253881;
+            g.j4 = -0.00000165597;
+            break;
+        case PERTURB_GPU_WGS84:
+            g.mus = 398600.5;
+            g.radiusearthkm = 6378.137;
+            g.xke = 60.0 / std::sqrt(g.radiusearthkm * g.radiusearthkm * g.radiusearthkm / g.mus);
+            g.j2 = 0.00108262998905;
+            g.j3 = -0.00000253215306;
+            g.j4 = -0.00000161098761;
+            break;
+        default: return false;
+    }
+    g.tumin = 1.0 / g.xke;
+    g.j3oj2 = g.j3 / g.j2;
+    return true;
+}
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct perturb_gpu_batch {
+    int device;
+    size_t n, n_pad;
+    pb::GravAll grav;
+    bool opsmode_a;
+
+    double *d_rec;     // [RF_COUNT][n]      caller order
+    double *d_pf;      // [PF_COUNT][n_pad]  class-sorted
+    int32_t *d_perm;   // [n_pad]
+    int tile_begin[PB_CLS_COUNT];
+    int tile_count[PB_CLS_COUNT];
+    std::vector<int32_t> init_error;
+    std::vector<uint8_t> cls;
+
+    // staging owned by the handle
+    cudaStream_t stream;       // compute stream used when the caller passes none
+    cudaStream_t copy_stream;  // D2H of host-resident outputs
+    double *d_times;
+    size_t times_cap;
+    double *d_stage[2];
+    int32_t *d_stage_err[2];
+    size_t stage_cap[2];  // evaluations each staging buffer holds
+    cudaEvent_t ev_done[2], ev_free[2];
+    int last_launches;
+
+    perturb_gpu_batch()
+        : device(0), n(0), n_pad(0), opsmode_a(false), d_rec(nullptr), d_pf(nullptr),
+          d_perm(nullptr), stream(nullptr), copy_stream(nullptr), d_times(nullptr),
+          times_cap(0), last_launches(0) {
+        for (int c = 0; c < PB_CLS_COUNT; ++c) tile_begin[c] = tile_count[c] = 0;
+        for (int b = 0; b < 2; ++b) {
+            d_stage[b] = nullptr;
+            d_stage_err[b] = nullptr;
+            stage_cap[b] = 0;
+            ev_done[b] = ev_free[b] = nullptr;
+        }
+    }
+};
+
+namespace {
+
+void destroy(perturb_gpu_batch *b) {
+    if (b == nullptr) return;
+    DeviceGuard guard(b->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->d_rec);
+    cudaFree(b->d_pf);
+    cudaFree(b->d_perm);
+    cudaFree(b->d_times);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(b->d_stage[i]);
+        cudaFree(b->d_stage_err[i]);
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+        if (b->ev_free[i]) cudaEventDestroy(b->ev_free[i]);
+    }
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    delete b;
+}
+
+// Classify + sort: stable counting sort by orbit class, every class padded to whole tiles.
+int build_sorted_layout(perturb_gpu_batch *b, double *d_pf_stage) {
+    const size_t n = b->n;
+    size_t count[PB_CLS_COUNT] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < n; ++i) count[std::min<int>(b->cls[i], PB_CLS_COUNT - 1)]++;
+    size_t slot = 0;
+    size_t first[PB_CLS_COUNT];
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        first[c] = slot;
+        b->tile_begin[c] = static_cast<int>(slot / PB_TILE_SATS);
+        const size_t tiles = (count[c] + PB_TILE_SATS - 1) / PB_TILE_SATS;
+        b->tile_count[c] = static_cast<int>(tiles);
+        slot += tiles * PB_TILE_SATS;
+    }
+    b->n_pad = slot;
+    std::vector<int32_t> perm(b->n_pad, -1);
+    size_t cursor[PB_CLS_COUNT];
+    for (int c = 0; c < PB_CLS_COUNT; ++c) cursor[c] = first[c];
+    for (size_t i = 0; i < n; ++i) {
+        const int c = std::min<int>(b->cls[i], PB_CLS_COUNT - 1);
+        perm[cursor[c]++] = static_cast<int32_t>(i);
+    }
+    if (b->n_pad == 0) return PERTURB_GPU_OK;
+    PB_CUDA(cudaMalloc(&b->d_perm, b->n_pad * sizeof(int32_t)));
+    PB_CUDA(cudaMalloc(&b->d_pf, b->n_pad * PF_COUNT * sizeof(double)));
+    PB_CUDA(cudaMemcpyAsync(b->d_perm, perm.data(), b->n_pad * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, b->stream));
+    pb::launch_pack(d_pf_stage, static_cast<int>(n), b->d_perm, static_cast<int>(b->n_pad),
+                    b->d_pf, b->stream);
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(b->stream));
+    return PERTURB_GPU_OK;
+}
+
+int create_common(size_t n, int grav_model, char opsmode, int device, perturb_gpu_batch **out,
+                  perturb_gpu_batch **made) {
+    if (out == nullptr) return fail(PERTURB_GPU_ERR_ARG, "out handle pointer is null");
+    *out = nullptr;
+    if (opsmode != 'i' && opsmode != 'a') {
+        return fail(PERTURB_GPU_ERR_ARG, "opsmode must be 'i' or 'a'");
+    }
+    if (n > static_cast<size_t>(1) << 30) return fail(PERTURB_GPU_ERR_ARG, "batch too large");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PERTURB_GPU_ERR_NODEV, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PERTURB_GPU_ERR_ARG, "bad device ordinal");
+    perturb_gpu_batch *b = new (std::nothrow) perturb_gpu_batch();
+    if (b == nullptr) return fail(PERTURB_GPU_ERR_ALLOC, "host allocation failed");
+    b->device = device;
+    b->n = n;
+    b->opsmode_a = (opsmode == 'a');
+    if (!gravity_constants(grav_model, b->grav)) {
+        delete b;
+        return fail(PERTURB_GPU_ERR_ARG, "unknown gravity model");
+    }
+    *made = b;
+    return PERTURB_GPU_OK;
+}
+
+int finish_create(perturb_gpu_batch *b, double *d_pf_stage, uint8_t *d_cls, int32_t *d_err,
+                  int32_t *init_error) {
+    const size_t n = b->n;
+    b->cls.assign(n, 0);
+    b->init_error.assign(n, 0);
+    if (n > 0) {
+        PB_CUDA(cudaMemcpyAsync(b->cls.data(), d_cls, n, cudaMemcpyDeviceToHost, b->stream));
+        PB_CUDA(cudaMemcpyAsync(b->init_error.data(), d_err, n * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, b->stream));
+        PB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    const int st = build_sorted_layout(b, d_pf_stage);
+    if (st != PERTURB_GPU_OK) return st;
+    if (init_error != nullptr && n > 0) {
+        std::memcpy(init_error, b->init_error.data(), n * sizeof(int32_t));
+    }
+    return PERTURB_GPU_OK;
+}
+
+int create_streams(perturb_gpu_batch *b) {
+    PB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PB_CUDA(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
+    }
+    return PERTURB_GPU_OK;
+}
+
+struct ScratchFree {
+    void *p[4];
+    ScratchFree() { p[0] = p[1] = p[2] = p[3] = nullptr; }
+    ~ScratchFree() {
+        for (int i = 0; i < 4; ++i) cudaFree(p[i]);
+    }
+};
+
+int init_impl(const void *src, bool from_records, size_t n, int grav_model, char opsmode,
+              int device, perturb_gpu_batch **out, int32_t *init_error) {
+    if (src == nullptr && n > 0) return fail(PERTURB_GPU_ERR_ARG, "input array is null");
+    perturb_gpu_batch *b = nullptr;
+    int st = create_common(n, grav_model, opsmode, device, out, &b);
+    if (st != PERTURB_GPU_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete b;
+        return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    }
+    struct Cleanup {
+        perturb_gpu_batch *b;
+        ~Cleanup() {
+            if (b) destroy(b);
+        }
+    } cleanup = {b};
+
+    st = create_streams(b);
+    if (st != PERTURB_GPU_OK) return st;
+
+    ScratchFree scratch;  // [0] input copy, [1] pf staging, [2] cls, [3] err
+    double *d_pf_stage = nullptr;
+    uint8_t *d_cls = nullptr;
+    int32_t *d_err = nullptr;
+    if (n > 0) {
+        PB_CUDA(cudaMalloc(&b->d_rec, n * RF_COUNT * sizeof(double)));
+        PB_CUDA(cudaMalloc(&scratch.p[1], n * PF_COUNT * sizeof(double)));
+        PB_CUDA(cudaMalloc(&scratch.p[2], n));
+        PB_CUDA(cudaMalloc(&scratch.p[3], n * sizeof(int32_t)));
+        d_pf_stage = static_cast<double *>(scratch.p[1]);
+        d_cls = static_cast<uint8_t *>(scratch.p[2]);
+        d_err = static_cast<int32_t *>(scratch.p[3]);
+
+        if (from_records) {
+            const size_t bytes = n * RF_COUNT * sizeof(double);
+            PB_CUDA(cudaMemcpyAsync(b->d_rec, src, bytes, cudaMemcpyDefault, b->stream));
+            pb::launch_derive_from_records(static_cast<int>(n), b->d_rec, d_pf_stage, d_cls,
+                                           d_err, b->stream);
+        } else {
+            const void *d_tles = src;
+            if (!is_device_pointer(src)) {
+                const size_t bytes = n * sizeof(perturb_gpu_tle);
+                PB_CUDA(cudaMalloc(&scratch.p[0], bytes));
+                PB_CUDA(cudaMemcpyAsync(scratch.p[0], src, bytes, cudaMemcpyHostToDevice,
+                                        b->stream));
+                d_tles = scratch.p[0];
+            }
+            pb::launch_sgp4init(d_tles, static_cast<int>(n), b->grav, b->opsmode_a, b->d_rec,
+                                d_pf_stage, d_cls, d_err, b->stream);
+        }
+        PB_CUDA(cudaGetLastError());
+    }
+    st = finish_create(b, d_pf_stage, d_cls, d_err, init_error);
+    if (st != PERTURB_GPU_OK) return st;
+    cleanup.b = nullptr;
+    *out = b;
+    return PERTURB_GPU_OK;
+}
+
+int ensure_times(perturb_gpu_batch *b, size_t m) {
+    if (b->times_cap >= m) return PERTURB_GPU_OK;
+    cudaFree(b->d_times);
+    b->d_times = nullptr;
+    b->times_cap = 0;
+    PB_CUDA(cudaMalloc(&b->d_times, 2 * m * sizeof(double)));
+    b->times_cap = m;
+    return PERTURB_GPU_OK;
+}
+
+int ensure_stage(perturb_gpu_batch *b, int which, size_t evals) {
+    if (b->stage_cap[which] >= evals) return PERTURB_GPU_OK;
+    cudaFree(b->d_stage[which]);
+    cudaFree(b->d_stage_err[which]);
+    b->d_stage[which] = nullptr;
+    b->d_stage_err[which] = nullptr;
+    b->stage_cap[which] = 0;
+    PB_CUDA(cudaMalloc(&b->d_stage[which], evals * 6 * sizeof(double)));
+    PB_CUDA(cudaMalloc(&b->d_stage_err[which], evals * sizeof(int32_t)));
+    b->stage_cap[which] = evals;
+    return PERTURB_GPU_OK;
+}
+
+void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
+    l.pf = b->d_pf;
+    l.n_pad = b->n_pad;
+    l.perm = b->d_perm;
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        l.tile_begin[c] = b->tile_begin[c];
+        l.tile_count[c] = b->tile_count[c];
+    }
+    l.radiusearthkm = b->grav.radiusearthkm;
+    l.xke = b->grav.xke;
+    l.j2 = b->grav.j2;
+    l.j3oj2 = b->grav.j3oj2;
+    l.opsmode_a = b->opsmode_a ? 1 : 0;
+}
+
+int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
+                   size_t m, double *posvel, int32_t *err, size_t row_stride,
+                   size_t plane_stride, void *stream_arg) {
+    if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    b->last_launches = 0;
+    if (m == 0 || b->n == 0) return PERTURB_GPU_OK;
+    if (ta == nullptr || (use_jd && tb == nullptr) || posvel == nullptr || err == nullptr) {
+        return fail(PERTURB_GPU_ERR_ARG, "null time or output pointer");
+    }
+    if (row_stride < m || plane_stride < b->n * row_stride) {
+        return fail(PERTURB_GPU_ERR_ARG, "row_stride < m or plane_stride < n * row_stride");
+    }
+    if (m > static_cast<size_t>(1) << 30) return fail(PERTURB_GPU_ERR_ARG, "time grid too long");
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t stream = stream_arg ? static_cast<cudaStream_t>(stream_arg) : b->stream;
+
+    // ---- time grid on the device ----
+    const bool ta_dev = is_device_pointer(ta);
+    const bool tb_dev = use_jd ? is_device_pointer(tb) : true;
+    const double *d_ta = ta, *d_tb = tb;
+    if (!ta_dev || !tb_dev) {
+        int st = ensure_times(b, m);
+        if (st != PERTURB_GPU_OK) return st;
+        if (!ta_dev) {
+            PB_CUDA(cudaMemcpyAsync(b->d_times, ta, m * sizeof(double), cudaMemcpyHostToDevice,
+                                    stream));
+            d_ta = b->d_times;
+        }
+        if (use_jd && !tb_dev) {
+            PB_CUDA(cudaMemcpyAsync(b->d_times + m, tb, m * sizeof(double),
+                                    cudaMemcpyHostToDevice, stream));
+            d_tb = b->d_times + m;
+        }
+    }
+
+    pb::PropLaunch l;
+    fill_launch(b, l);
+    l.use_jd = use_jd ? 1 : 0;
+
+    const bool out_dev = is_device_pointer(posvel);
+    const bool err_dev = is_device_pointer(err);
+    if (out_dev != err_dev) {
+        return fail(PERTURB_GPU_ERR_ARG, "posvel and err must both be host or both be device");
+    }
+
+    if (out_dev) {
+        l.ta = d_ta;
+        l.tb = d_tb;
+        l.m = static_cast<int>(m);
+        l.out = posvel;
+        l.plane_stride = plane_stride;
+        l.row_stride = row_stride;
+        l.err = err;
+        l.err_row_stride = row_stride;
+        b->last_launches = pb::launch_sgp4_propagate(l, stream);
+        PB_CUDA(cudaGetLastError());
+        return PERTURB_GPU_OK;
+    }
+
+    // ---- host outputs: time-chunked, double-buffered device staging + async D2H ----
+    size_t free_b = 0, total_b = 0;
+    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t bytes_per_eval = 6 * sizeof(double) + sizeof(int32_t);
+    size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(2) << 30);  // per buffer
+    for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * bytes_per_eval);
+    size_t mc = budget / (bytes_per_eval * b->n);
+    mc = std::min(mc, m);
+    mc &= ~static_cast<size_t>(1);  // even: keeps 16 B store alignment
+    if (mc < 2) mc = std::min<size_t>(m, 2);
+    const size_t mc_pad = (mc + 1) & ~static_cast<size_t>(1);
+    const size_t nchunks = (m + mc - 1) / mc;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    for (int i = 0; i < nbuf; ++i) {
+        int st = ensure_stage(b, i, b->n * mc_pad);
+        if (st != PERTURB_GPU_OK) return st;
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int buf = static_cast<int>(c % 2);
+        const size_t k0 = c * mc;
+        const size_t mk = std::min(mc, m - k0);
+        if (c >= 2) PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[buf], 0));
+        l.ta = d_ta + k0;
+        l.tb = use_jd ? d_tb + k0 : nullptr;
+        l.m = static_cast<int>(mk);
+        l.out = b->d_stage[buf];
+        l.row_stride = mc_pad;
+        l.plane_stride = b->n * mc_pad;
+        l.err = b->d_stage_err[buf];
+        l.err_row_stride = mc_pad;
+        b->last_launches += pb::launch_sgp4_propagate(l, stream);
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaEventRecord(b->ev_done[buf], stream));
+        PB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
+        for (int pl = 0; pl < 6; ++pl) {
+            PB_CUDA(cudaMemcpy2DAsync(posvel + pl * plane_stride + k0, row_stride * sizeof(double),
+                                      b->d_stage[buf] + pl * l.plane_stride,
+                                      mc_pad * sizeof(double), mk * sizeof(double), b->n,
+                                      cudaMemcpyDeviceToHost, b->copy_stream));
+        }
+        PB_CUDA(cudaMemcpy2DAsync(err + k0, row_stride * sizeof(int32_t), b->d_stage_err[buf],
+                                  mc_pad * sizeof(int32_t), mk * sizeof(int32_t), b->n,
+                                  cudaMemcpyDeviceToHost, b->copy_stream));
+        PB_CUDA(cudaEventRecord(b->ev_free[buf], b->copy_stream));
+    }
+    // The caller's stream must see the copies as part of this call.
+    const int last = static_cast<int>((nchunks - 1) % 2);
+    PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[last], 0));
+    if (nchunks > 1) PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[1 - last], 0));
+    return PERTURB_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int perturb_gpu_init(const perturb_gpu_tle *tles, size_t n, int grav_model, char opsmode,
+                     int device, perturb_gpu_batch **out, int32_t *init_error) {
+    return init_impl(tles, false, n, grav_model, opsmode, device, out, init_error);
+}
+
+int perturb_gpu_init_records(const double *records, size_t n, int grav_model, char opsmode,
+                             int device, perturb_gpu_batch **out, int32_t *init_error) {
+    return init_impl(records, true, n, grav_model, opsmode, device, out, init_error);
+}
+
+void perturb_gpu_free(perturb_gpu_batch *batch) { destroy(batch); }
+
+int perturb_gpu_propagate(perturb_gpu_batch *batch, const double *jd, const double *jd_frac,
+                          size_t m, double *posvel, int32_t *err, size_t row_stride,
+                          size_t plane_stride, void *stream) {
+    return propagate_impl(batch, jd, jd_frac, true, m, posvel, err, row_stride, plane_stride,
+                          stream);
+}
+
+int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *mins, size_t m,
+                                     double *posvel, int32_t *err, size_t row_stride,
+                                     size_t plane_stride, void *stream) {
+    return propagate_impl(batch, mins, nullptr, false, m, posvel, err, row_stride, plane_stride,
+                          stream);
+}
+
+int perturb_gpu_synchronize(perturb_gpu_batch *batch) {
+    if (batch == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    DeviceGuard guard(batch->device);
+    PB_CUDA(cudaStreamSynchronize(batch->stream));
+    PB_CUDA(cudaStreamSynchronize(batch->copy_stream));
+    return PERTURB_GPU_OK;
+}
+
+size_t perturb_gpu_size(const perturb_gpu_batch *batch) { return batch ? batch->n : 0; }
+
+int perturb_gpu_device(const perturb_gpu_batch *batch) { return batch ? batch->device : -1; }
+
+int perturb_gpu_last_error(const perturb_gpu_batch *batch, int32_t *out) {
+    if (batch == nullptr || out == nullptr) return fail(PERTURB_GPU_ERR_ARG, "null argument");
+    // convert_sgp4_error_code, src/perturb.cpp:24-29
+    for (size_t i = 0; i < batch->n; ++i) {
+        const int32_t c = batch->init_error[i];
+        out[i] = (c < 0 || c >= PERTURB_SGP4_UNKNOWN) ? PERTURB_SGP4_UNKNOWN : c;
+    }
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_orbit_class(const perturb_gpu_batch *batch, uint8_t *out) {
+    if (batch == nullptr || out == nullptr) return fail(PERTURB_GPU_ERR_ARG, "null argument");
+    if (batch->n) std::memcpy(out, batch->cls.data(), batch->n);
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_record_field_count(void) { return RF_COUNT; }
+
+const char *perturb_gpu_record_field_name(int field) {
+    return (field >= 0 && field < RF_COUNT) ? kRecordFieldNames[field] : nullptr;
+}
+
+int perturb_gpu_record_field(const perturb_gpu_batch *batch, int field, double *out) {
+    if (batch == nullptr || out == nullptr || field < 0 || field >= RF_COUNT) {
+        return fail(PERTURB_GPU_ERR_ARG, "bad argument");
+    }
+    if (batch->n == 0) return PERTURB_GPU_OK;
+    DeviceGuard guard(batch->device);
+    PB_CUDA(cudaMemcpy(out, batch->d_rec + static_cast<size_t>(field) * batch->n,
+                       batch->n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_epoch(const perturb_gpu_batch *batch, double *jd, double *jd_frac) {
+    int st = perturb_gpu_record_field(batch, RF_jdsatepoch, jd);
+    if (st != PERTURB_GPU_OK) return st;
+    return perturb_gpu_record_field(batch, RF_jdsatepochF, jd_frac);
+}
+
+int perturb_gpu_last_launch_count(const perturb_gpu_batch *batch) {
+    return batch ? batch->last_launches : 0;
+}
+
+const char *perturb_gpu_strerror(void) { return g_last_error.c_str(); }
+
+}  // extern "C"

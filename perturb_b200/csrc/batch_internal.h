@@ -1,0 +1,59 @@
+// Internal launch interface between the C-ABI (batch.cu) and the kernels.
+#ifndef PERTURB_B200_BATCH_INTERNAL_H
+#define PERTURB_B200_BATCH_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sgp4_fields.h"
+
+namespace pb {
+
+struct GravModelConsts;
+struct TleNumbers;
+
+struct GravAll {  // host copy of getgravconst(), src/sgp4.cpp:2101-2157
+    double tumin, mus, radiusearthkm, xke, j2, j3, j4, j3oj2;
+};
+
+// Kernel 1. tles: device AoS [n]; outputs: rec [RF_COUNT][n], pf_stage [PF_COUNT][n],
+// cls [n], init_error [n] (raw sgp4 codes, 7 for an invalid TLE).
+void launch_sgp4init(const void *d_tles, int n, const GravAll &g, bool opsmode_a, double *d_rec,
+                     double *d_pf_stage, uint8_t *d_cls, int32_t *d_init_error,
+                     cudaStream_t stream);
+
+// Alternate entry: records already initialised (by the caller's own sgp4init); only derives
+// the propagation fields and the class. init_error is taken from rec[RF_error].
+void launch_derive_from_records(int n, const double *d_rec, double *d_pf_stage, uint8_t *d_cls,
+                                int32_t *d_init_error, cudaStream_t stream);
+
+// Gather caller-order staging into the class-sorted propagation layout.
+// perm[slot] = caller index or -1 for padding slots.
+void launch_pack(const double *d_pf_stage, int n, const int32_t *d_perm, int n_pad,
+                 double *d_pf_sorted, cudaStream_t stream);
+
+struct PropLaunch {
+    const double *pf;  // [PF_COUNT][n_pad]
+    size_t n_pad;
+    const int32_t *perm;    // [n_pad]
+    int tile_begin[PB_CLS_COUNT];  // first 32-satellite tile of each class
+    int tile_count[PB_CLS_COUNT];
+    const double *ta;  // jd[m] or mins[m]   (device)
+    const double *tb;  // jd_frac[m] or null
+    int m;
+    int use_jd;
+    double *out;  // out[c * plane_stride + sat * row_stride + k], c = x,y,z,vx,vy,vz
+    size_t plane_stride, row_stride;
+    int32_t *err;  // err[sat * err_row_stride + k]
+    size_t err_row_stride;
+    double radiusearthkm, xke, j2, j3oj2;
+    int opsmode_a;
+};
+
+// Kernel 2, one launch per non-empty class. Returns the number of launches issued.
+int launch_sgp4_propagate(const PropLaunch &p, cudaStream_t stream);
+
+}  // namespace pb
+
+#endif

@@ -1,0 +1,414 @@
+// One SGP4/SDP4 evaluation: the device-side counterpart of
+//   sgp4::sgp4()  src/sgp4.cpp:1769-2065   (secular + drag, Kepler solve, short-period, TEME)
+//   dspace()      src/sgp4.cpp:1018-1166   (deep-space secular rates, resonance integrator)
+//   dpper('n')    src/sgp4.cpp:235-368     (lunar-solar periodics, Lyddane modification)
+// written for the propagation layout of sgp4_fields.h: per-satellite constants come from a
+// provider `K` (shared-memory tile in kernel 2, registers in kernel 1's epoch probe) and the
+// orbit class is a template parameter so each specialisation carries only its own terms.
+//
+// Differences from the reference, all value-preserving up to rounding:
+//   * stateless: the resonance integrator always starts from epoch (the reference's
+//     atime/xli/xni resume cache is an optimisation; restarted and resumed walks are
+//     bit-identical);
+//   * near-Earth: pow(xke/nm, 2/3) is per-satellite constant (nm == no_unkozai) and comes
+//     from PF_AOBASE; sin/cos(inclo) come from PF_SINIO/PF_COSIO;
+//   * bstar*cc4 and bstar*cc5 are hoisted (the reference evaluates them left to right, so
+//     the hoisted products are the same doubles).
+// The record fields the reference overwrites on every call (t, error, am..nm, and for deep
+// space aycof/xlcof/con41/x1mth2/x7thm1) are returned through `Sgp4Side` when asked for.
+#ifndef PERTURB_B200_SGP4_EVAL_CUH
+#define PERTURB_B200_SGP4_EVAL_CUH
+
+#include "sgp4_fields.h"
+#include "sgp4_math.cuh"
+
+namespace pb {
+
+// getgravconst() results the evaluation needs (src/sgp4.cpp:2101-2157), batch-wide.
+struct GravConsts {
+    double radiusearthkm, xke, j2, j3oj2, vkmpersec;
+};
+
+struct ClassFlags {  // used when CLS == PB_CLS_RUNTIME
+    bool deep, isimp;
+    int irez;
+};
+
+struct Sgp4Side {  // what sgp4() leaves in the record (src/sgp4.cpp:1895-1901, 1952-1957, 2017-2019)
+    double am, em, im, Om, om, mm, nm;
+    double aycof, xlcof, con41, x1mth2, x7thm1;
+    int stage;  // 0: nothing stored, 1: mean elements, 2: + aycof/xlcof, 3: + con41..x7thm1
+};
+
+template <int CLS>
+struct ClassTraits {
+    static constexpr bool kStatic = true;
+    static constexpr bool kDeep = (CLS >= PB_CLS_DEEP_NR);
+    static constexpr bool kSimp = (CLS != PB_CLS_NEAR_FULL);
+    static constexpr int kIrez =
+        (CLS == PB_CLS_DEEP_R1) ? 1 : (CLS == PB_CLS_DEEP_R2) ? 2 : 0;
+};
+template <>
+struct ClassTraits<PB_CLS_RUNTIME> {
+    static constexpr bool kStatic = false;
+    static constexpr bool kDeep = false, kSimp = false;
+    static constexpr int kIrez = 0;
+};
+
+// Resonance terms at one integrator node, src/sgp4.cpp:1097-1126.
+template <class K>
+__device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli, double xni,
+                                                double atime, double &xndt, double &xldot,
+                                                double &xnddt) {
+    if (irez != 2) {
+        constexpr double fasx2 = 0.13130908, fasx4 = 2.8843198, fasx6 = 0.37448087;
+        double s1, c1, s2, c2, s3, c3;
+        sincos_fast(xli - fasx2, s1, c1);
+        sincos_fast(2.0 * (xli - fasx4), s2, c2);
+        sincos_fast(3.0 * (xli - fasx6), s3, c3);
+        const double del1 = k(PF_DEL1), del2 = k(PF_DEL2), del3 = k(PF_DEL3);
+        xndt = del1 * s1 + del2 * s2 + del3 * s3;
+        xldot = xni + k(PF_XFACT);
+        xnddt = del1 * c1 + 2.0 * del2 * c2 + 3.0 * del3 * c3;
+        xnddt = xnddt * xldot;
+    } else {
+        constexpr double g22 = 5.7686396, g32 = 0.95240898, g44 = 1.8014998, g52 = 1.0508330,
+                         g54 = 4.4108898;
+        const double xomi = k(PF_ARGPO) + k(PF_ARGPDOT) * atime;
+        const double x2omi = xomi + xomi;
+        const double x2li = xli + xli;
+        double s, c, sa = 0.0, ca = 0.0, cb = 0.0;
+        sincos_fast(x2omi + xli - g22, s, c);
+        sa = k(PF_D2201) * s;
+        ca = k(PF_D2201) * c;
+        sincos_fast(xli - g22, s, c);
+        sa += k(PF_D2211) * s;
+        ca += k(PF_D2211) * c;
+        sincos_fast(xomi + xli - g32, s, c);
+        sa += k(PF_D3210) * s;
+        ca += k(PF_D3210) * c;
+        sincos_fast(-xomi + xli - g32, s, c);
+        sa += k(PF_D3222) * s;
+        ca += k(PF_D3222) * c;
+        sincos_fast(x2omi + x2li - g44, s, c);
+        sa += k(PF_D4410) * s;
+        cb = k(PF_D4410) * c;
+        sincos_fast(x2li - g44, s, c);
+        sa += k(PF_D4422) * s;
+        cb += k(PF_D4422) * c;
+        sincos_fast(xomi + xli - g52, s, c);
+        sa += k(PF_D5220) * s;
+        ca += k(PF_D5220) * c;
+        sincos_fast(-xomi + xli - g52, s, c);
+        sa += k(PF_D5232) * s;
+        ca += k(PF_D5232) * c;
+        sincos_fast(xomi + x2li - g54, s, c);
+        sa += k(PF_D5421) * s;
+        cb += k(PF_D5421) * c;
+        sincos_fast(-xomi + x2li - g54, s, c);
+        sa += k(PF_D5433) * s;
+        cb += k(PF_D5433) * c;
+        xndt = sa;
+        xldot = xni + k(PF_XFACT);
+        xnddt = (ca + 2.0 * cb) * xldot;
+    }
+}
+
+// Returns the raw sgp4 error code (0, 1, 2, 3, 4, 6). out[0..2] = r [km], out[3..5] = v
+// [km/s] are written for codes 0 and 6 only, exactly like the reference.
+template <int CLS, bool WANT_SIDE, class K>
+__device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool opsmode_a,
+                                         ClassFlags rt, double t, double out[6],
+                                         Sgp4Side *side) {
+    using T = ClassTraits<CLS>;
+    const bool deep = T::kStatic ? T::kDeep : rt.deep;
+    const bool simp = T::kStatic ? T::kSimp : rt.isimp;
+    const int irez = T::kStatic ? T::kIrez : rt.irez;
+    if (WANT_SIDE) side->stage = 0;
+
+    // ---- secular gravity and atmospheric drag, src/sgp4.cpp:1805-1835 ----
+    const double xmdf = k(PF_MO) + k(PF_MDOT) * t;
+    const double argpdf = k(PF_ARGPO) + k(PF_ARGPDOT) * t;
+    const double nodedf = k(PF_NODEO) + k(PF_NODEDOT) * t;
+    double argpm = argpdf;
+    double mm = xmdf;
+    const double t2 = t * t;
+    double nodem = nodedf + k(PF_NODECF) * t2;
+    double tempa = 1.0 - k(PF_CC1) * t;
+    double tempe = k(PF_BC4) * t;
+    double templ = k(PF_T2COF) * t2;
+
+    if (!simp) {
+        const double delomg = k(PF_OMGCOF) * t;
+        const double delmtemp = 1.0 + k(PF_ETA) * cos_fast(xmdf);
+        const double delm = k(PF_XMCOF) * (delmtemp * delmtemp * delmtemp - k(PF_DELMO));
+        const double temp = delomg + delm;
+        mm = xmdf + temp;
+        argpm = argpdf - temp;
+        const double t3 = t2 * t;
+        const double t4 = t3 * t;
+        tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
+        tempe = tempe + k(PF_BC5) * (sin_fast(mm) - k(PF_SINMAO));
+        templ = templ + k(PF_T3COF) * t3 + t4 * (k(PF_T4COF) + t * k(PF_T5COF));
+    }
+
+    const double no = k(PF_NO);
+    double nm = no;
+    double em = k(PF_ECCO);
+    double inclm = k(PF_INCLO);
+
+    // ---- dspace, src/sgp4.cpp:1018-1166 ----
+    if (deep) {
+        constexpr double rptim = 4.37526908801129966e-3;
+        const double theta = fmod_2pi(k(PF_GSTO) + t * rptim);
+        em = em + k(PF_DEDT) * t;
+        inclm = inclm + k(PF_DIDT) * t;
+        argpm = argpm + k(PF_DOMDT) * t;
+        nodem = nodem + k(PF_DNODT) * t;
+        mm = mm + k(PF_DMDT) * t;
+        if (irez != 0) {
+            double atime = 0.0, xni = no, xli = k(PF_XLAMO);
+            const double delt = (t > 0.0) ? 720.0 : -720.0;
+            double xndt, xldot, xnddt, ft;
+            int guard = 1 << 20;  // a non-finite t must not spin forever
+            for (;;) {
+                resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+                if (fabs(t - atime) >= 720.0 && --guard > 0) {
+                    xli = xli + xldot * delt + xndt * 259200.0;
+                    xni = xni + xndt * delt + xnddt * 259200.0;
+                    atime = atime + delt;
+                } else {
+                    ft = t - atime;
+                    break;
+                }
+            }
+            nm = xni + xndt * ft + xnddt * ft * ft * 0.5;
+            const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;
+            if (irez != 1) {
+                mm = xl - 2.0 * nodem + 2.0 * theta;
+            } else {
+                mm = xl - nodem - argpm + theta;
+            }
+            const double dndt = nm - no;
+            nm = no + dndt;
+        }
+    }
+
+    if (nm <= 0.0) return 2;  // :1860
+
+    double aobase;
+    if (deep && irez != 0) {
+        aobase = pow_2o3(g.xke / nm);
+    } else {
+        aobase = k(PF_AOBASE);  // nm == no_unkozai: pow(xke/no, 2/3) is a constant
+    }
+    const double am = aobase * tempa * tempa;
+    nm = g.xke / (am * sqrt(am));  // xke / pow(am, 1.5)
+    em = em - tempe;
+    if (em >= 1.0 || em < -0.001) return 1;  // :1873
+    if (em < 1.0e-6) em = 1.0e-6;
+    mm = mm + no * templ;
+    double xlm = mm + argpm + nodem;
+
+    nodem = fmod_2pi(nodem);
+    argpm = fmod_2pi(argpm);
+    xlm = fmod_2pi(xlm);
+    mm = fmod_2pi(xlm - argpm - nodem);
+
+    if (WANT_SIDE) {
+        side->am = am;
+        side->em = em;
+        side->im = inclm;
+        side->Om = nodem;
+        side->om = argpm;
+        side->mm = mm;
+        side->nm = nm;
+        side->stage = 1;
+    }
+
+    // ---- lunar-solar periodics, src/sgp4.cpp:1908-1958 with dpper :235-368 ----
+    double ep = em, xincp = inclm, argpp = argpm, nodep = nodem, mp = mm;
+    double sinip, cosip, aycof, xlcof;
+    if (deep) {
+        constexpr double zns = 1.19459e-5, zes = 0.01675, znl = 1.5835218e-4, zel = 0.05490;
+        double zm, zf, sinzf, coszf, f2, f3, s0, c0;
+        zm = k(PF_ZMOS) + zns * t;
+        zf = zm + 2.0 * zes * sin_fast(zm);
+        sincos_fast(zf, sinzf, coszf);
+        f2 = 0.5 * sinzf * sinzf - 0.25;
+        f3 = -0.5 * sinzf * coszf;
+        const double ses = k(PF_SE2) * f2 + k(PF_SE3) * f3;
+        const double sis = k(PF_SI2) * f2 + k(PF_SI3) * f3;
+        const double sls = k(PF_SL2) * f2 + k(PF_SL3) * f3 + k(PF_SL4) * sinzf;
+        const double sghs = k(PF_SGH2) * f2 + k(PF_SGH3) * f3 + k(PF_SGH4) * sinzf;
+        const double shs = k(PF_SH2) * f2 + k(PF_SH3) * f3;
+        zm = k(PF_ZMOL) + znl * t;
+        zf = zm + 2.0 * zel * sin_fast(zm);
+        sincos_fast(zf, sinzf, coszf);
+        f2 = 0.5 * sinzf * sinzf - 0.25;
+        f3 = -0.5 * sinzf * coszf;
+        const double sel = k(PF_EE2) * f2 + k(PF_E3) * f3;
+        const double sil = k(PF_XI2) * f2 + k(PF_XI3) * f3;
+        const double sll = k(PF_XL2) * f2 + k(PF_XL3) * f3 + k(PF_XL4) * sinzf;
+        const double sghl = k(PF_XGH2) * f2 + k(PF_XGH3) * f3 + k(PF_XGH4) * sinzf;
+        const double shll = k(PF_XH2) * f2 + k(PF_XH3) * f3;
+        // peo, pinco, plo, pgho, pho are zero after dscom (:494-498)
+        const double pe = ses + sel;
+        const double pinc = sis + sil;
+        const double pl = sls + sll;
+        double pgh = sghs + sghl;
+        double ph = shs + shll;
+        xincp = xincp + pinc;
+        ep = ep + pe;
+        sincos_fast(xincp, s0, c0);
+        if (xincp >= 0.2) {  // :317
+            ph = ph / s0;
+            pgh = pgh - c0 * ph;
+            argpp = argpp + pgh;
+            nodep = nodep + ph;
+            mp = mp + pl;
+        } else {  // Lyddane modification, :325-364
+            double sinop, cosop;
+            sincos_fast(nodep, sinop, cosop);
+            double alfdp = s0 * sinop;
+            double betdp = s0 * cosop;
+            const double dalf = ph * cosop + pinc * c0 * sinop;
+            const double dbet = -ph * sinop + pinc * c0 * cosop;
+            alfdp = alfdp + dalf;
+            betdp = betdp + dbet;
+            nodep = fmod_2pi(nodep);
+            if (nodep < 0.0 && opsmode_a) nodep = nodep + kTwoPi;
+            double xls = mp + argpp + c0 * nodep;
+            const double dls = pl + pgh - pinc * nodep * s0;
+            xls = xls + dls;
+            const double xnoh = nodep;
+            nodep = atan2(alfdp, betdp);
+            if (nodep < 0.0 && opsmode_a) nodep = nodep + kTwoPi;
+            if (fabs(xnoh - nodep) > kPi) {
+                if (nodep < xnoh) {
+                    nodep = nodep + kTwoPi;
+                } else {
+                    nodep = nodep - kTwoPi;
+                }
+            }
+            mp = mp + pl;
+            argpp = xls - mp - c0 * nodep;
+        }
+        if (xincp < 0.0) {  // :1932
+            xincp = -xincp;
+            nodep = nodep + kPi;
+            argpp = argpp - kPi;
+        }
+        if (ep < 0.0 || ep > 1.0) return 3;  // :1938
+        sincos_fast(xincp, sinip, cosip);
+        aycof = -0.5 * g.j3oj2 * sinip;
+        if (fabs(cosip + 1.0) > 1.5e-12) {
+            xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / (1.0 + cosip);
+        } else {
+            xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / 1.5e-12;
+        }
+        if (WANT_SIDE) {
+            side->aycof = aycof;
+            side->xlcof = xlcof;
+            side->stage = 2;
+        }
+    } else {
+        sinip = k(PF_SINIO);
+        cosip = k(PF_COSIO);
+        aycof = k(PF_AYCOF);
+        xlcof = k(PF_XLCOF);
+    }
+
+    // ---- long-period periodics and Kepler's equation, src/sgp4.cpp:1959-1983 ----
+    double sinargp, cosargp;
+    sincos_fast(argpp, sinargp, cosargp);
+    const double axnl = ep * cosargp;
+    double temp = 1.0 / (am * (1.0 - ep * ep));
+    const double aynl = ep * sinargp + temp * aycof;
+    const double xl = mp + argpp + nodep + temp * xlcof * axnl;
+
+    const double u = fmod_2pi(xl - nodep);
+    double eo1 = u, tem5 = 9999.9, sineo1 = 1.0, coseo1 = 1.0;
+    int ktr = 1;
+    while (fabs(tem5) >= 1.0e-12 && ktr <= 10) {
+        sincos_fast(eo1, sineo1, coseo1);
+        tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
+        tem5 = (u - aynl * coseo1 + axnl * sineo1 - eo1) / tem5;
+        if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
+        eo1 = eo1 + tem5;
+        ktr = ktr + 1;
+    }
+
+    // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
+    const double ecose = axnl * coseo1 + aynl * sineo1;
+    const double esine = axnl * sineo1 - aynl * coseo1;
+    const double el2 = axnl * axnl + aynl * aynl;
+    const double pl = am * (1.0 - el2);
+    if (pl < 0.0) return 4;  // :1990
+
+    const double rl = am * (1.0 - ecose);
+    const double rdotl = sqrt(am) * esine / rl;
+    const double rvdotl = sqrt(pl) / rl;
+    const double betal = sqrt(1.0 - el2);
+    temp = esine / (1.0 + betal);
+    const double aorl = am / rl;
+    const double sinu = aorl * (sineo1 - aynl - axnl * temp);
+    const double cosu = aorl * (coseo1 - axnl + aynl * temp);
+    double su = atan2(sinu, cosu);
+    const double sin2u = (cosu + cosu) * sinu;
+    const double cos2u = 1.0 - 2.0 * sinu * sinu;
+    temp = 1.0 / pl;
+    const double temp1 = 0.5 * g.j2 * temp;
+    const double temp2 = temp1 * temp;
+
+    double con41, x1mth2, x7thm1;
+    if (deep) {  // :2014-2020
+        const double cosisq = cosip * cosip;
+        con41 = 3.0 * cosisq - 1.0;
+        x1mth2 = 1.0 - cosisq;
+        x7thm1 = 7.0 * cosisq - 1.0;
+        if (WANT_SIDE) {
+            side->con41 = con41;
+            side->x1mth2 = x1mth2;
+            side->x7thm1 = x7thm1;
+            side->stage = 3;
+        }
+    } else {
+        con41 = k(PF_CON41);
+        x1mth2 = k(PF_X1MTH2);
+        x7thm1 = k(PF_X7THM1);
+    }
+    const double mrt = rl * (1.0 - 1.5 * temp2 * betal * con41) + 0.5 * temp1 * x1mth2 * cos2u;
+    su = su - 0.25 * temp2 * x7thm1 * sin2u;
+    const double xnode = nodep + 1.5 * temp2 * cosip * sin2u;
+    const double xinc = xincp + 1.5 * temp2 * cosip * sinip * cos2u;
+    const double mvt = rdotl - nm * temp1 * x1mth2 * sin2u / g.xke;
+    const double rvdot = rvdotl + nm * temp1 * (x1mth2 * cos2u + 1.5 * con41) / g.xke;
+
+    // ---- orientation vectors, position and velocity, src/sgp4.cpp:2031-2052 ----
+    double sinsu, cossu, snod, cnod, sini, cosi;
+    sincos_fast(su, sinsu, cossu);
+    sincos_fast(xnode, snod, cnod);
+    sincos_fast(xinc, sini, cosi);
+    const double xmx = -snod * cosi;
+    const double xmy = cnod * cosi;
+    const double ux = xmx * sinsu + cnod * cossu;
+    const double uy = xmy * sinsu + snod * cossu;
+    const double uz = sini * sinsu;
+    const double vx = xmx * cossu - cnod * sinsu;
+    const double vy = xmy * cossu - snod * sinsu;
+    const double vz = sini * cossu;
+
+    out[0] = (mrt * ux) * g.radiusearthkm;
+    out[1] = (mrt * uy) * g.radiusearthkm;
+    out[2] = (mrt * uz) * g.radiusearthkm;
+    out[3] = (mvt * ux + rvdot * vx) * g.vkmpersec;
+    out[4] = (mvt * uy + rvdot * vy) * g.vkmpersec;
+    out[5] = (mvt * uz + rvdot * vz) * g.vkmpersec;
+
+    return (mrt < 1.0) ? 6 : 0;  // :2056
+}
+
+}  // namespace pb
+
+#endif
