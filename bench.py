@@ -271,6 +271,18 @@ def run_gpu(args):
     evals_step_rank = float(n) * m
     value = evals_step_rank * world * args.steps / (max_ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            ms = max_ms / args.steps
+            print(json.dumps({"quick": True, "lib": os.path.basename(pb.capi.LIB_PATH),
+                              "workload": args.workload, "value": value, "ms_per_step": ms,
+                              "tflops_v0": falg * evals_step_rank / (total_ms / args.steps * 1e-3) * 1e-12,
+                              "fp64_peak": fp64_peak, "clocks": clocks,
+                              "classes": cls.tolist(), "launches": launches_per_step}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the C ABI with HOST buffers ----
     h_jd = torch.tensor(jd).pin_memory()
     h_fr = torch.tensor(fr).pin_memory()
@@ -386,6 +398,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--quick", action="store_true",
+                    help="device-resident timing only (no e2e, no CPU arm): kernel tuning sweeps")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -156,6 +156,11 @@ int perturb_gpu_last_launch_count(const perturb_gpu_batch *batch);
  * best of 5 after a warm-up; *tflops counts a DFMA as 2 flops. Used by bench.py. */
 int perturb_gpu_measure_fp64_peak(int device, double *tflops);
 
+/* Test hook: out[i] = f(x[i], y[i]) for the device math routine number `fn` (see
+ * perturb_b200/csrc/math_probe.cu); host pointers. Lets the test-suite bound the error of
+ * the FP64 fast paths against correctly rounded host values. */
+int perturb_gpu_math_probe(int fn, const double *x, const double *y, double *out, size_t n);
+
 /* Message for the most recent failure on the calling thread. */
 const char *perturb_gpu_strerror(void);
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libperturb_gpu.so")
+LIB_PATH = os.environ.get("PERTURB_GPU_LIB") or os.path.join(_HERE, "libperturb_gpu.so")
 
 OK = 0
 WGS72_OLD, WGS72, WGS84 = 0, 1, 2
@@ -32,7 +32,7 @@ EXPORTS = (
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles "
-    "perturb_gpu_measure_fp64_peak "
+    "perturb_gpu_measure_fp64_peak perturb_gpu_math_probe "
     "perturb_synth_catalog perturb_synth_time_grid"
 ).split()
 
@@ -75,6 +75,7 @@ def lib():
     L.perturb_gpu_last_launch_count.argtypes = [vp]
     L.perturb_gpu_strerror.restype = C.c_char_p
     L.perturb_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    L.perturb_gpu_math_probe.argtypes = [C.c_int, dp, dp, dp, C.c_size_t]
     L.perturb_gpu_parse_tles.argtypes = [
         C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Tle), ip]
     L.perturb_synth_catalog.argtypes = [

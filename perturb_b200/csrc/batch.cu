@@ -110,7 +110,8 @@ struct perturb_gpu_batch {
     std::vector<uint8_t> cls;
 
     // staging owned by the handle
-    cudaStream_t stream;       // compute stream used when the caller passes none
+    cudaStream_t stream;       // construction-time work (kernel 1, sort, pack)
+    cudaStream_t last_stream;  // stream of the most recent propagate call
     cudaStream_t copy_stream;  // D2H of host-resident outputs
     double *d_times;
     size_t times_cap;
@@ -118,13 +119,29 @@ struct perturb_gpu_batch {
     int32_t *d_stage_err[2];
     size_t stage_cap[2];  // evaluations each staging buffer holds
     cudaEvent_t ev_done[2], ev_free[2];
+    double2 *d_res_nodes;  // resonance node table [res_cap][resonant slots]
+    int *d_res_k0, *d_res_cnt;
+    double *d_res_range;
+    int res_cap;
+    cudaStream_t aux[PB_CLS_COUNT];  // forked streams, one per orbit class
+    cudaEvent_t ev_fork, ev_join[PB_CLS_COUNT];
     int last_launches;
 
     perturb_gpu_batch()
         : device(0), n(0), n_pad(0), opsmode_a(false), d_rec(nullptr), d_pf(nullptr),
-          d_perm(nullptr), stream(nullptr), copy_stream(nullptr), d_times(nullptr),
+          d_perm(nullptr), stream(nullptr), last_stream(nullptr), copy_stream(nullptr),
+          d_times(nullptr),
           times_cap(0), last_launches(0) {
-        for (int c = 0; c < PB_CLS_COUNT; ++c) tile_begin[c] = tile_count[c] = 0;
+        for (int c = 0; c < PB_CLS_COUNT; ++c) {
+            tile_begin[c] = tile_count[c] = 0;
+            aux[c] = nullptr;
+            ev_join[c] = nullptr;
+        }
+        ev_fork = nullptr;
+        d_res_nodes = nullptr;
+        d_res_k0 = d_res_cnt = nullptr;
+        d_res_range = nullptr;
+        res_cap = 0;
         for (int b = 0; b < 2; ++b) {
             d_stage[b] = nullptr;
             d_stage_err[b] = nullptr;
@@ -150,6 +167,15 @@ void destroy(perturb_gpu_batch *b) {
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
         if (b->ev_free[i]) cudaEventDestroy(b->ev_free[i]);
     }
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        if (b->aux[c]) cudaStreamDestroy(b->aux[c]);
+        if (b->ev_join[c]) cudaEventDestroy(b->ev_join[c]);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    cudaFree(b->d_res_nodes);
+    cudaFree(b->d_res_k0);
+    cudaFree(b->d_res_cnt);
+    cudaFree(b->d_res_range);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
@@ -232,6 +258,19 @@ int finish_create(perturb_gpu_batch *b, double *d_pf_stage, uint8_t *d_cls, int3
     if (init_error != nullptr && n > 0) {
         std::memcpy(init_error, b->init_error.data(), n * sizeof(int32_t));
     }
+    // Resonance node table: 64 nodes (32 days of grid span) per resonant satellite, less if
+    // that would exceed 1 GiB; times outside the table integrate in-line (same bits, slower).
+    const size_t res_slots = static_cast<size_t>(b->tile_count[PB_CLS_DEEP_R1] +
+                                                 b->tile_count[PB_CLS_DEEP_R2]) * PB_TILE_SATS;
+    if (res_slots > 0) {
+        size_t cap = 64;
+        while (cap > 4 && cap * res_slots * sizeof(double2) > (static_cast<size_t>(1) << 30)) cap /= 2;
+        PB_CUDA(cudaMalloc(&b->d_res_nodes, cap * res_slots * sizeof(double2)));
+        PB_CUDA(cudaMalloc(&b->d_res_k0, res_slots * sizeof(int)));
+        PB_CUDA(cudaMalloc(&b->d_res_cnt, res_slots * sizeof(int)));
+        PB_CUDA(cudaMalloc(&b->d_res_range, 4 * sizeof(double)));
+        b->res_cap = static_cast<int>(cap);
+    }
     return PERTURB_GPU_OK;
 }
 
@@ -241,6 +280,11 @@ int create_streams(perturb_gpu_batch *b) {
     for (int i = 0; i < 2; ++i) {
         PB_CUDA(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
         PB_CUDA(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
+    }
+    PB_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        PB_CUDA(cudaStreamCreateWithFlags(&b->aux[c], cudaStreamNonBlocking));
+        PB_CUDA(cudaEventCreateWithFlags(&b->ev_join[c], cudaEventDisableTiming));
     }
     return PERTURB_GPU_OK;
 }
@@ -349,6 +393,16 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
     l.j2 = b->grav.j2;
     l.j3oj2 = b->grav.j3oj2;
     l.opsmode_a = b->opsmode_a ? 1 : 0;
+    l.res_nodes = b->d_res_nodes;
+    l.res_k0 = b->d_res_k0;
+    l.res_cnt = b->d_res_cnt;
+    l.res_range = b->d_res_range;
+    l.res_cap = b->res_cap;
+    l.fork = b->ev_fork;
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        l.aux[c] = b->aux[c];
+        l.join[c] = b->ev_join[c];
+    }
 }
 
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
@@ -366,7 +420,9 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     if (m > static_cast<size_t>(1) << 30) return fail(PERTURB_GPU_ERR_ARG, "time grid too long");
     DeviceGuard guard(b->device);
     if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t stream = stream_arg ? static_cast<cudaStream_t>(stream_arg) : b->stream;
+    // NULL is the (legacy) default stream, as in the CUDA runtime API.
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_arg);
+    b->last_stream = stream;
 
     // ---- time grid on the device ----
     const bool ta_dev = is_device_pointer(ta);
@@ -496,7 +552,7 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
 int perturb_gpu_synchronize(perturb_gpu_batch *batch) {
     if (batch == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
     DeviceGuard guard(batch->device);
-    PB_CUDA(cudaStreamSynchronize(batch->stream));
+    PB_CUDA(cudaStreamSynchronize(batch->last_stream));
     PB_CUDA(cudaStreamSynchronize(batch->copy_stream));
     return PERTURB_GPU_OK;
 }

@@ -49,6 +49,15 @@ struct PropLaunch {
     size_t err_row_stride;
     double radiusearthkm, xke, j2, j3oj2;
     int opsmode_a;
+    // resonance node table scratch (null / 0: resonant evaluations integrate in-line)
+    double2 *res_nodes;  // [res_cap][resonant slots]
+    int *res_k0, *res_cnt;
+    double *res_range;   // [4]
+    int res_cap;
+    // optional fork/join resources so class launches overlap (null = serial on one stream)
+    cudaStream_t aux[PB_CLS_COUNT];
+    cudaEvent_t fork;
+    cudaEvent_t join[PB_CLS_COUNT];
 };
 
 // Kernel 2, one launch per non-empty class. Returns the number of launches issued.

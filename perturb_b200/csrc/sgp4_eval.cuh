@@ -13,7 +13,9 @@
 //   * near-Earth: pow(xke/nm, 2/3) is per-satellite constant (nm == no_unkozai) and comes
 //     from PF_AOBASE; sin/cos(inclo) come from PF_SINIO/PF_COSIO;
 //   * bstar*cc4 and bstar*cc5 are hoisted (the reference evaluates them left to right, so
-//     the hoisted products are the same doubles).
+//     the hoisted products are the same doubles);
+//   * libm calls are replaced by the range-bounded routines of sgp4_math.cuh, divisions by
+//     reciprocal-multiply, and atan2 + sincos of the argument of latitude by a rotation.
 // The record fields the reference overwrites on every call (t, error, am..nm, and for deep
 // space aycof/xlcof/con41/x1mth2/x7thm1) are returned through `Sgp4Side` when asked for.
 #ifndef PERTURB_B200_SGP4_EVAL_CUH
@@ -26,7 +28,7 @@ namespace pb {
 
 // getgravconst() results the evaluation needs (src/sgp4.cpp:2101-2157), batch-wide.
 struct GravConsts {
-    double radiusearthkm, xke, j2, j3oj2, vkmpersec;
+    double radiusearthkm, xke, j2, j3oj2, vkmpersec, inv_xke;
 };
 
 struct ClassFlags {  // used when CLS == PB_CLS_RUNTIME
@@ -55,7 +57,9 @@ struct ClassTraits<PB_CLS_RUNTIME> {
     static constexpr int kIrez = 0;
 };
 
-// Resonance terms at one integrator node, src/sgp4.cpp:1097-1126.
+// Resonance terms at one integrator node, src/sgp4.cpp:1097-1126. Written with explicit
+// fused operations: the node table (built by a pre-pass kernel) and the in-line fall-back
+// must produce the same bits no matter how the compiler would contract either copy.
 template <class K>
 __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli, double xni,
                                                 double atime, double &xndt, double &xldot,
@@ -63,63 +67,100 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
     if (irez != 2) {
         constexpr double fasx2 = 0.13130908, fasx4 = 2.8843198, fasx6 = 0.37448087;
         double s1, c1, s2, c2, s3, c3;
-        sincos_fast(xli - fasx2, s1, c1);
-        sincos_fast(2.0 * (xli - fasx4), s2, c2);
-        sincos_fast(3.0 * (xli - fasx6), s3, c3);
+        sincos_cw(wrap_pi2(__dsub_rn(xli, fasx2)), s1, c1);
+        sincos_cw(wrap_pi2(__dmul_rn(2.0, __dsub_rn(xli, fasx4))), s2, c2);
+        sincos_cw(wrap_pi2(__dmul_rn(3.0, __dsub_rn(xli, fasx6))), s3, c3);
         const double del1 = k(PF_DEL1), del2 = k(PF_DEL2), del3 = k(PF_DEL3);
-        xndt = del1 * s1 + del2 * s2 + del3 * s3;
-        xldot = xni + k(PF_XFACT);
-        xnddt = del1 * c1 + 2.0 * del2 * c2 + 3.0 * del3 * c3;
-        xnddt = xnddt * xldot;
+        xndt = __fma_rn(del3, s3, __fma_rn(del2, s2, __dmul_rn(del1, s1)));
+        xldot = __dadd_rn(xni, k(PF_XFACT));
+        xnddt = __fma_rn(__dmul_rn(3.0, del3), c3,
+                         __fma_rn(__dmul_rn(2.0, del2), c2, __dmul_rn(del1, c1)));
+        xnddt = __dmul_rn(xnddt, xldot);
     } else {
         constexpr double g22 = 5.7686396, g32 = 0.95240898, g44 = 1.8014998, g52 = 1.0508330,
                          g54 = 4.4108898;
-        const double xomi = k(PF_ARGPO) + k(PF_ARGPDOT) * atime;
-        const double x2omi = xomi + xomi;
-        const double x2li = xli + xli;
-        double s, c, sa = 0.0, ca = 0.0, cb = 0.0;
-        sincos_fast(x2omi + xli - g22, s, c);
-        sa = k(PF_D2201) * s;
-        ca = k(PF_D2201) * c;
-        sincos_fast(xli - g22, s, c);
-        sa += k(PF_D2211) * s;
-        ca += k(PF_D2211) * c;
-        sincos_fast(xomi + xli - g32, s, c);
-        sa += k(PF_D3210) * s;
-        ca += k(PF_D3210) * c;
-        sincos_fast(-xomi + xli - g32, s, c);
-        sa += k(PF_D3222) * s;
-        ca += k(PF_D3222) * c;
-        sincos_fast(x2omi + x2li - g44, s, c);
-        sa += k(PF_D4410) * s;
-        cb = k(PF_D4410) * c;
-        sincos_fast(x2li - g44, s, c);
-        sa += k(PF_D4422) * s;
-        cb += k(PF_D4422) * c;
-        sincos_fast(xomi + xli - g52, s, c);
-        sa += k(PF_D5220) * s;
-        ca += k(PF_D5220) * c;
-        sincos_fast(-xomi + xli - g52, s, c);
-        sa += k(PF_D5232) * s;
-        ca += k(PF_D5232) * c;
-        sincos_fast(xomi + x2li - g54, s, c);
-        sa += k(PF_D5421) * s;
-        cb += k(PF_D5421) * c;
-        sincos_fast(-xomi + x2li - g54, s, c);
-        sa += k(PF_D5433) * s;
-        cb += k(PF_D5433) * c;
+        const double xomi = __fma_rn(k(PF_ARGPDOT), atime, k(PF_ARGPO));
+        const double x2omi = __dadd_rn(xomi, xomi);
+        const double x2li = __dadd_rn(xli, xli);
+        const double a22 = __dsub_rn(xli, g22), a32 = __dsub_rn(xli, g32);
+        const double a52 = __dsub_rn(xli, g52), a44 = __dsub_rn(x2li, g44);
+        const double a54 = __dsub_rn(x2li, g54);
+        double s, c, sa, ca, cb;
+        sincos_cw(wrap_pi2(__dadd_rn(x2omi, a22)), s, c);
+        sa = __dmul_rn(k(PF_D2201), s);
+        ca = __dmul_rn(k(PF_D2201), c);
+        sincos_cw(wrap_pi2(a22), s, c);
+        sa = __fma_rn(k(PF_D2211), s, sa);
+        ca = __fma_rn(k(PF_D2211), c, ca);
+        sincos_cw(wrap_pi2(__dadd_rn(xomi, a32)), s, c);
+        sa = __fma_rn(k(PF_D3210), s, sa);
+        ca = __fma_rn(k(PF_D3210), c, ca);
+        sincos_cw(wrap_pi2(__dsub_rn(a32, xomi)), s, c);
+        sa = __fma_rn(k(PF_D3222), s, sa);
+        ca = __fma_rn(k(PF_D3222), c, ca);
+        sincos_cw(wrap_pi2(__dadd_rn(x2omi, a44)), s, c);
+        sa = __fma_rn(k(PF_D4410), s, sa);
+        cb = __dmul_rn(k(PF_D4410), c);
+        sincos_cw(wrap_pi2(a44), s, c);
+        sa = __fma_rn(k(PF_D4422), s, sa);
+        cb = __fma_rn(k(PF_D4422), c, cb);
+        sincos_cw(wrap_pi2(__dadd_rn(xomi, a52)), s, c);
+        sa = __fma_rn(k(PF_D5220), s, sa);
+        ca = __fma_rn(k(PF_D5220), c, ca);
+        sincos_cw(wrap_pi2(__dsub_rn(a52, xomi)), s, c);
+        sa = __fma_rn(k(PF_D5232), s, sa);
+        ca = __fma_rn(k(PF_D5232), c, ca);
+        sincos_cw(wrap_pi2(__dadd_rn(xomi, a54)), s, c);
+        sa = __fma_rn(k(PF_D5421), s, sa);
+        cb = __fma_rn(k(PF_D5421), c, cb);
+        sincos_cw(wrap_pi2(__dsub_rn(a54, xomi)), s, c);
+        sa = __fma_rn(k(PF_D5433), s, sa);
+        cb = __fma_rn(k(PF_D5433), c, cb);
         xndt = sa;
-        xldot = xni + k(PF_XFACT);
-        xnddt = (ca + 2.0 * cb) * xldot;
+        xldot = __dadd_rn(xni, k(PF_XFACT));
+        xnddt = __dmul_rn(__fma_rn(2.0, cb, ca), xldot);
     }
 }
+
+// One +-720 min Euler-Maclaurin step of the resonance integrator, src/sgp4.cpp:1143-1145.
+__device__ __forceinline__ void resonance_advance(double xndt, double xldot, double xnddt,
+                                                  double delt, double &xli, double &xni,
+                                                  double &atime) {
+    xli = __fma_rn(xndt, 259200.0, __fma_rn(xldot, delt, xli));
+    xni = __fma_rn(xnddt, 259200.0, __fma_rn(xndt, delt, xni));
+    atime = __dadd_rn(atime, delt);
+}
+
+// Number of whole 720-minute steps the reference's loop `while (fabs(t - atime) >= 720)`
+// takes from epoch (src/sgp4.cpp:1093-1147): floor(|t| / 720), decided on the exact
+// remainder |t| - 720 n (exactly representable) so that the count is the reference's.
+__device__ __forceinline__ int resonance_step_count(double t) {
+    const double at = fabs(t);
+    if (!(at < 1.0e9)) return 0;  // non-finite or absurd time: garbage in, no spinning
+    int n = static_cast<int>(at * (1.0 / 720.0));
+    const double rem = __fma_rn(-720.0, static_cast<double>(n), at);
+    if (rem >= 720.0) {
+        ++n;
+    } else if (rem < 0.0) {
+        --n;
+    }
+    return n;
+}
+
+// Integrator states tabulated per satellite by the pre-pass kernel: node j holds (xli, xni)
+// after (k0 + j) steps from epoch (negative = backwards).
+struct ResNodes {
+    const double2 *base;  // this satellite's column: element j at base[j * stride]
+    size_t stride;
+    int k0, count;
+};
 
 // Returns the raw sgp4 error code (0, 1, 2, 3, 4, 6). out[0..2] = r [km], out[3..5] = v
 // [km/s] are written for codes 0 and 6 only, exactly like the reference.
 template <int CLS, bool WANT_SIDE, class K>
 __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool opsmode_a,
                                          ClassFlags rt, double t, double out[6],
-                                         Sgp4Side *side) {
+                                         Sgp4Side *side, const ResNodes *nodes = nullptr) {
     using T = ClassTraits<CLS>;
     const bool deep = T::kStatic ? T::kDeep : rt.deep;
     const bool simp = T::kStatic ? T::kSimp : rt.isimp;
@@ -140,7 +181,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     if (!simp) {
         const double delomg = k(PF_OMGCOF) * t;
-        const double delmtemp = 1.0 + k(PF_ETA) * cos_fast(xmdf);
+        const double delmtemp = 1.0 + k(PF_ETA) * cos_cw(wrap_pi2(xmdf));
         const double delm = k(PF_XMCOF) * (delmtemp * delmtemp * delmtemp - k(PF_DELMO));
         const double temp = delomg + delm;
         mm = xmdf + temp;
@@ -148,7 +189,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double t3 = t2 * t;
         const double t4 = t3 * t;
         tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
-        tempe = tempe + k(PF_BC5) * (sin_fast(mm) - k(PF_SINMAO));
+        tempe = tempe + k(PF_BC5) * (sin_cw(wrap_pi2(mm)) - k(PF_SINMAO));
         templ = templ + k(PF_T3COF) * t3 + t4 * (k(PF_T4COF) + t * k(PF_T5COF));
     }
 
@@ -167,21 +208,31 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         nodem = nodem + k(PF_DNODT) * t;
         mm = mm + k(PF_DMDT) * t;
         if (irez != 0) {
-            double atime = 0.0, xni = no, xli = k(PF_XLAMO);
+            // Stateless restart from epoch (== the reference's `atime = 0` branch, :1079-1084).
+            // n whole steps, then the partial step ft. With a node table the n steps are one
+            // 16 B load; otherwise (kernel 1's epoch probe, or a time outside the table) they
+            // are integrated here with the very same operations.
+            const int n = resonance_step_count(t);
             const double delt = (t > 0.0) ? 720.0 : -720.0;
-            double xndt, xldot, xnddt, ft;
-            int guard = 1 << 20;  // a non-finite t must not spin forever
-            for (;;) {
-                resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
-                if (fabs(t - atime) >= 720.0 && --guard > 0) {
-                    xli = xli + xldot * delt + xndt * 259200.0;
-                    xni = xni + xndt * delt + xnddt * 259200.0;
-                    atime = atime + delt;
-                } else {
-                    ft = t - atime;
-                    break;
+            const int kk = (t > 0.0) ? n : -n;
+            double atime, xni, xli;
+            double xndt, xldot, xnddt;
+            if (nodes != nullptr && kk >= nodes->k0 && kk < nodes->k0 + nodes->count) {
+                const double2 st = nodes->base[static_cast<size_t>(kk - nodes->k0) * nodes->stride];
+                xli = st.x;
+                xni = st.y;
+                atime = __dmul_rn(delt, static_cast<double>(n));
+            } else {
+                atime = 0.0;
+                xni = no;
+                xli = k(PF_XLAMO);
+                for (int i = 0; i < n; ++i) {
+                    resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+                    resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
                 }
             }
+            resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            const double ft = t - atime;
             nm = xni + xndt * ft + xnddt * ft * ft * 0.5;
             const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;
             if (irez != 1) {
@@ -198,22 +249,35 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     double aobase;
     if (deep && irez != 0) {
-        aobase = pow_2o3(g.xke / nm);
+        aobase = pow_2o3(div_fast(g.xke, nm));
     } else {
         aobase = k(PF_AOBASE);  // nm == no_unkozai: pow(xke/no, 2/3) is a constant
     }
     const double am = aobase * tempa * tempa;
-    nm = g.xke / (am * sqrt(am));  // xke / pow(am, 1.5)
+    const double rsqrt_am = rsqrt_fast(am);
+    const double sqrt_am = am * rsqrt_am;
+    nm = g.xke * (rsqrt_am * rsqrt_am * rsqrt_am);  // xke / pow(am, 1.5)
     em = em - tempe;
     if (em >= 1.0 || em < -0.001) return 1;  // :1873
     if (em < 1.0e-6) em = 1.0e-6;
     mm = mm + no * templ;
     double xlm = mm + argpm + nodem;
 
-    nodem = fmod_2pi(nodem);
-    argpm = fmod_2pi(argpm);
-    xlm = fmod_2pi(xlm);
-    mm = fmod_2pi(xlm - argpm - nodem);
+    if (deep || WANT_SIDE) {
+        // dpper multiplies nodep itself by cos(i) in the Lyddane branch (:341) and compares it
+        // against atan2 output (:352): the representative matters, keep C fmod semantics. The
+        // same holds when the mean elements are handed back to the record (Om, om, mm).
+        nodem = fmod_2pi(nodem);
+        argpm = fmod_2pi(argpm);
+        xlm = fmod_2pi(xlm);
+        mm = fmod_2pi(xlm - argpm - nodem);
+    } else {
+        // near-Earth: these angles only enter sin/cos and sums that are reduced again
+        nodem = wrap_pi(nodem);
+        argpm = wrap_pi(argpm);
+        xlm = wrap_pi(xlm);
+        mm = wrap_pi(xlm - argpm - nodem);
+    }
 
     if (WANT_SIDE) {
         side->am = am;
@@ -233,8 +297,8 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         constexpr double zns = 1.19459e-5, zes = 0.01675, znl = 1.5835218e-4, zel = 0.05490;
         double zm, zf, sinzf, coszf, f2, f3, s0, c0;
         zm = k(PF_ZMOS) + zns * t;
-        zf = zm + 2.0 * zes * sin_fast(zm);
-        sincos_fast(zf, sinzf, coszf);
+        zf = zm + 2.0 * zes * sin_cw(wrap_pi2(zm));
+        sincos_cw(wrap_pi2(zf), sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
         const double ses = k(PF_SE2) * f2 + k(PF_SE3) * f3;
@@ -243,8 +307,8 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double sghs = k(PF_SGH2) * f2 + k(PF_SGH3) * f3 + k(PF_SGH4) * sinzf;
         const double shs = k(PF_SH2) * f2 + k(PF_SH3) * f3;
         zm = k(PF_ZMOL) + znl * t;
-        zf = zm + 2.0 * zel * sin_fast(zm);
-        sincos_fast(zf, sinzf, coszf);
+        zf = zm + 2.0 * zel * sin_cw(wrap_pi2(zm));
+        sincos_cw(wrap_pi2(zf), sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
         const double sel = k(PF_EE2) * f2 + k(PF_E3) * f3;
@@ -260,16 +324,16 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         double ph = shs + shll;
         xincp = xincp + pinc;
         ep = ep + pe;
-        sincos_fast(xincp, s0, c0);
+        sincos_cw(wrap_pi2(xincp), s0, c0);
         if (xincp >= 0.2) {  // :317
-            ph = ph / s0;
+            ph = div_fast(ph, s0);
             pgh = pgh - c0 * ph;
             argpp = argpp + pgh;
             nodep = nodep + ph;
             mp = mp + pl;
         } else {  // Lyddane modification, :325-364
             double sinop, cosop;
-            sincos_fast(nodep, sinop, cosop);
+            sincos_cw(wrap_pi2(nodep), sinop, cosop);
             double alfdp = s0 * sinop;
             double betdp = s0 * cosop;
             const double dalf = ph * cosop + pinc * c0 * sinop;
@@ -300,10 +364,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             argpp = argpp - kPi;
         }
         if (ep < 0.0 || ep > 1.0) return 3;  // :1938
-        sincos_fast(xincp, sinip, cosip);
+        sincos_cw(wrap_pi2(xincp), sinip, cosip);
         aycof = -0.5 * g.j3oj2 * sinip;
         if (fabs(cosip + 1.0) > 1.5e-12) {
-            xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / (1.0 + cosip);
+            xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), 1.0 + cosip);
         } else {
             xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / 1.5e-12;
         }
@@ -321,19 +385,19 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     // ---- long-period periodics and Kepler's equation, src/sgp4.cpp:1959-1983 ----
     double sinargp, cosargp;
-    sincos_fast(argpp, sinargp, cosargp);
+    sincos_cw(deep ? wrap_pi2(argpp) : argpp, sinargp, cosargp);
     const double axnl = ep * cosargp;
-    double temp = 1.0 / (am * (1.0 - ep * ep));
+    double temp = rcp_fast(am * (1.0 - ep * ep));
     const double aynl = ep * sinargp + temp * aycof;
     const double xl = mp + argpp + nodep + temp * xlcof * axnl;
 
-    const double u = fmod_2pi(xl - nodep);
+    const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
     double eo1 = u, tem5 = 9999.9, sineo1 = 1.0, coseo1 = 1.0;
     int ktr = 1;
     while (fabs(tem5) >= 1.0e-12 && ktr <= 10) {
-        sincos_fast(eo1, sineo1, coseo1);
+        sincos_cw(eo1, sineo1, coseo1);
         tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
-        tem5 = (u - aynl * coseo1 + axnl * sineo1 - eo1) / tem5;
+        tem5 = div_fast(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
         eo1 = eo1 + tem5;
         ktr = ktr + 1;
@@ -347,17 +411,17 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     if (pl < 0.0) return 4;  // :1990
 
     const double rl = am * (1.0 - ecose);
-    const double rdotl = sqrt(am) * esine / rl;
-    const double rvdotl = sqrt(pl) / rl;
-    const double betal = sqrt(1.0 - el2);
-    temp = esine / (1.0 + betal);
-    const double aorl = am / rl;
+    const double inv_rl = rcp_fast(rl);
+    const double rdotl = sqrt_am * esine * inv_rl;
+    const double rvdotl = sqrt_fast(pl) * inv_rl;
+    const double betal = sqrt_fast(1.0 - el2);
+    temp = esine * rcp_fast(1.0 + betal);
+    const double aorl = am * inv_rl;
     const double sinu = aorl * (sineo1 - aynl - axnl * temp);
     const double cosu = aorl * (coseo1 - axnl + aynl * temp);
-    double su = atan2(sinu, cosu);
     const double sin2u = (cosu + cosu) * sinu;
     const double cos2u = 1.0 - 2.0 * sinu * sinu;
-    temp = 1.0 / pl;
+    temp = rcp_fast(pl);
     const double temp1 = 0.5 * g.j2 * temp;
     const double temp2 = temp1 * temp;
 
@@ -379,17 +443,30 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         x7thm1 = k(PF_X7THM1);
     }
     const double mrt = rl * (1.0 - 1.5 * temp2 * betal * con41) + 0.5 * temp1 * x1mth2 * cos2u;
-    su = su - 0.25 * temp2 * x7thm1 * sin2u;
+    // The reference forms su = atan2(sinu, cosu) - dsu and then takes sin(su), cos(su)
+    // (:2006, 2023, 2031-2032). Only those two are used, so rotate the unit vector
+    // (sinu, cosu)/hypot by the small angle dsu instead: no atan2, no second range reduction.
+    const double dsu = 0.25 * temp2 * x7thm1 * sin2u;
     const double xnode = nodep + 1.5 * temp2 * cosip * sin2u;
     const double xinc = xincp + 1.5 * temp2 * cosip * sinip * cos2u;
-    const double mvt = rdotl - nm * temp1 * x1mth2 * sin2u / g.xke;
-    const double rvdot = rvdotl + nm * temp1 * (x1mth2 * cos2u + 1.5 * con41) / g.xke;
+    const double nmt = nm * temp1 * g.inv_xke;
+    const double mvt = rdotl - nmt * x1mth2 * sin2u;
+    const double rvdot = rvdotl + nmt * (x1mth2 * cos2u + 1.5 * con41);
 
     // ---- orientation vectors, position and velocity, src/sgp4.cpp:2031-2052 ----
     double sinsu, cossu, snod, cnod, sini, cosi;
-    sincos_fast(su, sinsu, cossu);
-    sincos_fast(xnode, snod, cnod);
-    sincos_fast(xinc, sini, cosi);
+    {
+        const double h2 = sinu * sinu + cosu * cosu;
+        const double inv_h = (h2 > 0.0) ? rsqrt_fast(h2) : 0.0;
+        const double su_s = (h2 > 0.0) ? sinu * inv_h : 0.0;  // atan2(0, 0) == 0
+        const double su_c = (h2 > 0.0) ? cosu * inv_h : 1.0;
+        double sd, cd;
+        sincos_small(dsu, sd, cd);
+        sinsu = su_s * cd - su_c * sd;
+        cossu = su_c * cd + su_s * sd;
+    }
+    sincos_cw(deep ? wrap_pi2(xnode) : xnode, snod, cnod);
+    sincos_cw(deep ? wrap_pi2(xinc) : xinc, sini, cosi);
     const double xmx = -snod * cosi;
     const double xmy = cnod * cosi;
     const double ux = xmx * sinsu + cnod * cossu;

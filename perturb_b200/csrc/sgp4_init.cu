@@ -21,6 +21,7 @@ __device__ void epoch_probe(SatRec &rec, const double pf[PF_COUNT], bool opsmode
     g.j2 = rec.f[RF_j2];
     g.j3oj2 = rec.f[RF_j3oj2];
     g.vkmpersec = g.radiusearthkm * g.xke / 60.0;
+    g.inv_xke = 1.0 / g.xke;
     ClassFlags fl;
     fl.deep = rec.f[RF_method_d] != 0.0;
     fl.isimp = rec.f[RF_isimp] != 0.0;

@@ -1,14 +1,21 @@
 // Device FP64 math for the SGP4/SDP4 kernels (sm_100a).
 //
 // The reference calls glibc's sin/cos/fmod/pow/atan2 (L0 of the layer map). On B200 the
-// path is FP64-pipe bound, so the kernels use range-bounded fast paths:
-//   * sincos: 3-constant Cody-Waite reduction + minimax kernels on [-pi/4, pi/4], with a
-//     (warp-uniformly not taken) fall-back to libdevice for |x| >= 1e5;
+// path is FP64-pipe bound and -- measured with ncu on the first version -- issue bound: of
+// ~1475 warp instructions per evaluation only ~560 were FP64, the rest were constant
+// materialisation (UMOV/IMAD.MOV pairs for every double literal), slow-path guards of
+// libdevice div/sqrt/sincos and quadrant logic. Hence:
+//   * every polynomial coefficient lives in __constant__ memory, so DFMA takes it as a
+//     constant-bank operand instead of two moves;
+//   * sincos: 3-constant Cody-Waite reduction + minimax kernels on [-pi/4, pi/4], no slow
+//     path: callers pass angles that are already reduced (or reduce them with wrap_pi2);
+//     single sin / cos select ONE coefficient set by quadrant parity instead of evaluating both;
 //   * fmod(x, 2pi): one FMA-exact reduction with the C `fmod` sign convention (libdevice's
-//     fmod is a bit-serial integer loop: 0 FP64 but ~144 integer instructions);
+//     fmod is a bit-serial integer loop); wrap_pi where only the angle mod 2pi matters;
+//   * division / sqrt: MUFU seed + Newton steps, no denormal/overflow fix-up call;
 //   * pow(x, 2/3) -> cbrt(x)^2, pow(x, 1.5) -> x*sqrt(x).
 // None of these is bit-identical to glibc; the parity budget (1e-6 km, 1e-9 km/s) leaves
-// about five decimal orders over their rounding error (tests/test_gpu_parity.py).
+// about three decimal orders over their rounding error (tests/test_gpu_parity.py).
 #ifndef PERTURB_B200_SGP4_MATH_CUH
 #define PERTURB_B200_SGP4_MATH_CUH
 
@@ -18,86 +25,216 @@ namespace pb {
 
 constexpr double kPi = 3.14159265358979323846;  // src/sgp4.cpp:69
 constexpr double kTwoPi = 2.0 * kPi;
-constexpr double kInvTwoPi = 1.0 / kTwoPi;
-constexpr double kRintMagic = 6755399441055744.0;  // 1.5 * 2^52
 
+// Constant-bank table (index names below). Kept in one array so that the compiler addresses
+// it as c[3][imm] operands.
+enum {
+    MC_RINT_MAGIC = 0,  // 1.5 * 2^52
+    MC_INV_TWOPI,
+    MC_TWOPI,
+    MC_TWOPI_LO,        // 2pi - (double)2pi
+    MC_TWO_OVER_PI,
+    MC_PIO2_HI,
+    MC_PIO2_MID,
+    MC_PIO2_LO,
+    MC_S1, MC_S2, MC_S3, MC_S4, MC_S5, MC_S6,  // sin kernel, fdlibm minimax set
+    MC_C1, MC_C2, MC_C3, MC_C4, MC_C5, MC_C6,  // cos kernel
+    MC_HALF,
+    MC_ONE,
+    MC_COUNT
+};
+
+static __constant__ double kMc[MC_COUNT] = {
+    6755399441055744.0,
+    0.15915494309189534561,
+    6.28318530717958647692,
+    2.4492935982947064e-16,
+    6.36619772367581382433e-01,
+    1.5707963267948966e+00,
+    6.1232339957367574e-17,
+    8.4784276603688985e-32,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    0.5,
+    1.0,
+};
+
+// ---- reciprocal, division, square root ---------------------------------------------------
+// MUFU.RCP64H / MUFU.RSQ64H seeds (about 20 good bits) refined by Newton steps. Inputs on
+// this path are normal, finite doubles; zero / infinity / NaN propagate as NaN or infinity
+// garbage exactly where the reference produces garbage too.
+__device__ __forceinline__ double rcp_fast(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = __fma_rn(-b, r, kMc[MC_ONE]);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-b, r, kMc[MC_ONE]);
+    r = __fma_rn(r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double div_fast(double a, double b) {
+    const double r = rcp_fast(b);
+    const double q = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-b, q, a), r, q);  // one correction step: <= 1 ulp
+}
+
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // y <- y * (1.5 - 0.5 x y^2), twice
+    double h = __dmul_rn(x, kMc[MC_HALF]);
+    double e = __fma_rn(-__dmul_rn(h, y), y, kMc[MC_HALF]);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-__dmul_rn(h, y), y, kMc[MC_HALF]);
+    y = __fma_rn(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ double sqrt_fast(double x) {
+    if (x == 0.0) return 0.0;
+    const double y = rsqrt_fast(x);
+    const double s = __dmul_rn(x, y);
+    // s <- s + 0.5 y (x - s^2)
+    return __fma_rn(__dmul_rn(y, kMc[MC_HALF]), __fma_rn(-s, s, x), s);
+}
+
+// ---- angle reduction -----------------------------------------------------------------------
 // x mod 2pi with the sign of x (C fmod semantics), exact: q = rint(x/2pi) may be off by one
 // from trunc(x/2pi), but x - q*2pi is a multiple of 2^-50 below 8 in magnitude, so the FMA
 // and the +-2pi fix-ups are all exact and the result is the unique representative fmod returns.
 __device__ __forceinline__ double fmod_2pi(double x) {
-    const double q = __dadd_rn(__fma_rn(x, kInvTwoPi, kRintMagic), -kRintMagic);
-    double r = __fma_rn(-q, kTwoPi, x);
+    const double q = __dadd_rn(__fma_rn(x, kMc[MC_INV_TWOPI], kMc[MC_RINT_MAGIC]),
+                               -kMc[MC_RINT_MAGIC]);
+    double r = __fma_rn(-q, kMc[MC_TWOPI], x);
     if (x >= 0.0) {
-        if (r < 0.0) r = __dadd_rn(r, kTwoPi);
+        if (r < 0.0) r = __dadd_rn(r, kMc[MC_TWOPI]);
     } else {
-        if (r > 0.0) r = __dadd_rn(r, -kTwoPi);
+        if (r > 0.0) r = __dadd_rn(r, -kMc[MC_TWOPI]);
     }
     return r;
 }
 
-// Same reduction without the sign fix-up: result in [-pi, pi], congruent to x mod 2pi.
-// For consumers that only feed the angle to sin/cos or to sums that are reduced again.
+// Same reduction modulo the DOUBLE 2pi without the sign fix-up: result in [-pi, pi]. For
+// angles the reference reduces with fmod(x, twopi) and then only feeds to sin/cos or to sums
+// that are reduced again (every near-Earth use).
 __device__ __forceinline__ double wrap_pi(double x) {
-    const double q = __dadd_rn(__fma_rn(x, kInvTwoPi, kRintMagic), -kRintMagic);
-    return __fma_rn(-q, kTwoPi, x);
+    const double q = __dadd_rn(__fma_rn(x, kMc[MC_INV_TWOPI], kMc[MC_RINT_MAGIC]),
+                               -kMc[MC_RINT_MAGIC]);
+    return __fma_rn(-q, kMc[MC_TWOPI], x);
 }
 
-namespace detail {
-// minimax kernels on [-pi/4, pi/4] (the classic fdlibm coefficient sets)
-__device__ __forceinline__ double sin_kernel(double r, double z) {
-    double p = 1.58969099521155010221e-10;
-    p = __fma_rn(p, z, -2.50507602534068634195e-08);
-    p = __fma_rn(p, z, 2.75573137070700676789e-06);
-    p = __fma_rn(p, z, -1.98412698298579493134e-04);
-    p = __fma_rn(p, z, 8.33333333332248946124e-03);
-    p = __fma_rn(p, z, -1.66666666666666324348e-01);
-    return __fma_rn(__dmul_rn(r, z), p, r);
+// Reduction modulo the TRUE 2pi (two-term constant): for angles the reference hands
+// unreduced to sin/cos (xmdf and mm grow like n*t, ~700 rad after a week).
+__device__ __forceinline__ double wrap_pi2(double x) {
+    const double q = __dadd_rn(__fma_rn(x, kMc[MC_INV_TWOPI], kMc[MC_RINT_MAGIC]),
+                               -kMc[MC_RINT_MAGIC]);
+    const double r = __fma_rn(-q, kMc[MC_TWOPI], x);
+    return __fma_rn(-q, kMc[MC_TWOPI_LO], r);
 }
-__device__ __forceinline__ double cos_kernel(double z) {
-    double p = -1.13596475577881948265e-11;
-    p = __fma_rn(p, z, 2.08757232129817482790e-09);
-    p = __fma_rn(p, z, -2.75573143513906633035e-07);
-    p = __fma_rn(p, z, 2.48015872894767294178e-05);
-    p = __fma_rn(p, z, -1.38888888888741095749e-03);
-    p = __fma_rn(p, z, 4.16666666666666019037e-02);
-    return __fma_rn(__dmul_rn(z, z), p, __fma_rn(-0.5, z, 1.0));
+
+// ---- sin / cos ---------------------------------------------------------------------------
+namespace detail {
+// Quadrant k = rint(x * 2/pi) and reduced argument r = x - k*pi/2 (three-term pi/2).
+// Valid for |x| < ~1e5 (k < 2^17); callers guarantee that by reducing first.
+__device__ __forceinline__ double reduce_pio2(double x, int &q) {
+    const double kd = __fma_rn(x, kMc[MC_TWO_OVER_PI], kMc[MC_RINT_MAGIC]);
+    q = __double2loint(kd);
+    const double k = __dadd_rn(kd, -kMc[MC_RINT_MAGIC]);
+    double r = __fma_rn(-k, kMc[MC_PIO2_HI], x);
+    r = __fma_rn(-k, kMc[MC_PIO2_MID], r);
+    r = __fma_rn(-k, kMc[MC_PIO2_LO], r);
+    return r;
+}
+__device__ __forceinline__ double sin_poly(double z) {
+    double p = kMc[MC_S6];
+    p = __fma_rn(p, z, kMc[MC_S5]);
+    p = __fma_rn(p, z, kMc[MC_S4]);
+    p = __fma_rn(p, z, kMc[MC_S3]);
+    p = __fma_rn(p, z, kMc[MC_S2]);
+    p = __fma_rn(p, z, kMc[MC_S1]);
+    return p;
+}
+__device__ __forceinline__ double cos_poly(double z) {
+    double p = kMc[MC_C6];
+    p = __fma_rn(p, z, kMc[MC_C5]);
+    p = __fma_rn(p, z, kMc[MC_C4]);
+    p = __fma_rn(p, z, kMc[MC_C3]);
+    p = __fma_rn(p, z, kMc[MC_C2]);
+    p = __fma_rn(p, z, kMc[MC_C1]);
+    return p;
+}
+__device__ __forceinline__ double flip_sign(double v, int neg) {
+    // XOR the sign bit: integer pipe, not FP64
+    const int hi = __double2hiint(v) ^ (neg << 31);
+    return __hiloint2double(hi, __double2loint(v));
 }
 }  // namespace detail
 
-// sin and cos of x together. Fast path valid for |x| < 1e5 (k < 2^17, so the three-term
-// pi/2 expansion leaves < 1e-27 absolute error in the reduced argument).
-__device__ __forceinline__ void sincos_fast(double x, double &s, double &c) {
-    if (!(fabs(x) < 1.0e5)) {  // also catches NaN
-        sincos(x, &s, &c);
-        return;
-    }
-    const double kd = __fma_rn(x, 6.36619772367581382433e-01, kRintMagic);
-    const int q = __double2loint(kd);
-    const double k = __dadd_rn(kd, -kRintMagic);
-    double r = __fma_rn(-k, 1.5707963267948966e+00, x);
-    r = __fma_rn(-k, 6.1232339957367574e-17, r);
-    r = __fma_rn(-k, 8.4784276603688985e-32, r);
+// sin and cos of a reduced angle (|x| < 1e5, normally |x| <= 2pi + small).
+__device__ __forceinline__ void sincos_cw(double x, double &s, double &c) {
+    int q;
+    const double r = detail::reduce_pio2(x, q);
     const double z = __dmul_rn(r, r);
-    const double sr = detail::sin_kernel(r, z);
-    const double cr = detail::cos_kernel(z);
-    double ss = (q & 1) ? cr : sr;
-    double cc = (q & 1) ? sr : cr;
-    if (q & 2) ss = -ss;
-    if ((q + 1) & 2) cc = -cc;
-    s = ss;
-    c = cc;
+    const double sr = __fma_rn(__dmul_rn(r, z), detail::sin_poly(z), r);
+    const double cr = __fma_rn(__dmul_rn(z, z), detail::cos_poly(z),
+                               __fma_rn(-kMc[MC_HALF], z, kMc[MC_ONE]));
+    const bool odd = (q & 1) != 0;
+    const double ss = odd ? cr : sr;
+    const double cc = odd ? sr : cr;
+    s = detail::flip_sign(ss, (q >> 1) & 1);
+    c = detail::flip_sign(cc, ((q + 1) >> 1) & 1);
 }
 
-__device__ __forceinline__ double sin_fast(double x) {
-    double s, c;
-    sincos_fast(x, s, c);
-    return s;
+// One of sin/cos only: which kernel is needed depends on quadrant parity, and both kernels
+// have the same Horner shape, so the coefficients are selected and ONE polynomial is run.
+template <bool WANT_COS>
+__device__ __forceinline__ double sin_or_cos_cw(double x) {
+    int q;
+    const double r = detail::reduce_pio2(x, q);
+    if (WANT_COS) q += 1;  // cos(x) = sin(x + pi/2)
+    const bool use_cos = (q & 1) != 0;
+    const double z = __dmul_rn(r, r);
+    double p = use_cos ? kMc[MC_C6] : kMc[MC_S6];
+    p = __fma_rn(p, z, use_cos ? kMc[MC_C5] : kMc[MC_S5]);
+    p = __fma_rn(p, z, use_cos ? kMc[MC_C4] : kMc[MC_S4]);
+    p = __fma_rn(p, z, use_cos ? kMc[MC_C3] : kMc[MC_S3]);
+    p = __fma_rn(p, z, use_cos ? kMc[MC_C2] : kMc[MC_S2]);
+    p = __fma_rn(p, z, use_cos ? kMc[MC_C1] : kMc[MC_S1]);
+    // sin: r + (r z) p        cos: (1 - z/2) + (z z) p
+    const double lead = use_cos ? __fma_rn(-kMc[MC_HALF], z, kMc[MC_ONE]) : r;
+    const double scale = __dmul_rn(use_cos ? z : r, z);
+    const double v = __fma_rn(scale, p, lead);
+    return detail::flip_sign(v, (q >> 1) & 1);
 }
 
-__device__ __forceinline__ double cos_fast(double x) {
-    double s, c;
-    sincos_fast(x, s, c);
-    return c;
+__device__ __forceinline__ double sin_cw(double x) { return sin_or_cos_cw<false>(x); }
+__device__ __forceinline__ double cos_cw(double x) { return sin_or_cos_cw<true>(x); }
+
+// sin and cos of a small angle (|d| < 2^-6) by short Taylor sums; anything larger goes
+// through the general routine. Used for the short-period correction of the argument of
+// latitude, |d| ~ 1e-3 for every physical orbit.
+__device__ __forceinline__ void sincos_small(double d, double &s, double &c) {
+    if (fabs(d) < 0.015625) {
+        const double z = __dmul_rn(d, d);
+        // sin d = d (1 - z/6 + z^2/120 - z^3/5040 + z^4/362880), error < 1e-24
+        double p = 2.75573192239858906526e-06;
+        p = __fma_rn(p, z, -1.98412698412698412698e-04);
+        p = __fma_rn(p, z, 8.33333333333333333333e-03);
+        p = __fma_rn(p, z, -1.66666666666666666667e-01);
+        s = __fma_rn(__dmul_rn(d, z), p, d);
+        // cos d = 1 - z/2 + z^2/24 - z^3/720 + z^4/40320 - z^5/3628800
+        double k = -2.75573192239858906526e-07;
+        k = __fma_rn(k, z, 2.48015873015873015873e-05);
+        k = __fma_rn(k, z, -1.38888888888888888889e-03);
+        k = __fma_rn(k, z, 4.16666666666666666667e-02);
+        k = __fma_rn(k, z, -0.5);
+        c = __fma_rn(k, z, 1.0);
+    } else {
+        sincos_cw(wrap_pi2(d), s, c);
+    }
 }
 
 // pow(x, 2/3) for x > 0 (the reference passes x2o3 = 2.0/3.0, src/sgp4.cpp:1795, 1867)

@@ -19,7 +19,19 @@ namespace pb {
 
 namespace {
 
-constexpr int kWarps = 4;                      // warps per CTA
+// Resident CTAs per SM the register allocation is capped for (measured on B200, sweep in
+// profiles/r1_sweeps.md): near-Earth bodies fit 80 registers with a handful of spills and
+// gain from 24 warps/SM; the deep-space bodies are larger and do best at 4 CTAs (128 regs).
+#ifndef PB_MIN_BLOCKS_NEAR
+#define PB_MIN_BLOCKS_NEAR 6
+#endif
+#ifndef PB_MIN_BLOCKS_DEEP
+#define PB_MIN_BLOCKS_DEEP 4
+#endif
+#ifndef PB_WARPS
+#define PB_WARPS 4
+#endif
+constexpr int kWarps = PB_WARPS;               // warps per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kTpl = 2;                        // times per lane
 constexpr int kTimeTile = kThreads * kTpl;     // times per CTA
@@ -66,16 +78,136 @@ struct PropParams {
     int vec_ok;
     GravConsts g;
     int opsmode_a;
+    // resonance node table (deep-space resonant classes only)
+    const double2 *res_nodes;  // [res_cap][res_stride]
+    const int *res_k0;         // [res_stride] first tabulated step index per resonant slot
+    const int *res_cnt;        // [res_stride] number of tabulated nodes
+    size_t res_stride;         // resonant slots (padded)
+    size_t res_first_slot;     // sorted slot of the first resonant satellite
 };
 
+struct GlobalConsts {  // constants of one sorted slot straight from the field-major layout
+    const double *base;
+    size_t stride;
+    __device__ __forceinline__ double operator()(int f) const { return base[f * stride]; }
+};
+
+// tsince of a grid time for one satellite: Satellite::propagate, src/perturb.cpp:237-238 with
+// JulianDate::operator- (:80-83); propagate_from_epoch passes minutes through.
+__device__ __forceinline__ double tsince_of(int use_jd, double ta, double tb, double jd0,
+                                            double jdf0) {
+    if (!use_jd) return ta;
+    return __dmul_rn(__dadd_rn(__dsub_rn(ta, jd0), __dsub_rn(tb, jdf0)), 1440.0);
+}
+
+// Pre-pass 1: earliest and latest time of the grid -> range[0..3] = (ta, tb) of the earliest,
+// (ta, tb) of the latest. One CTA; the grid is at most a few 10^5 entries.
+__global__ void __launch_bounds__(256)
+time_range_kernel(const double *__restrict__ ta, const double *__restrict__ tb, int m, int use_jd,
+                  double *__restrict__ range) {
+    __shared__ double s_lo[256], s_hi[256];
+    __shared__ int s_ilo[256], s_ihi[256];
+    const double ref_a = ta[0], ref_b = use_jd ? tb[0] : 0.0;
+    double lo = 0.0, hi = 0.0;
+    int ilo = 0, ihi = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double d = (ta[i] - ref_a) + ((use_jd ? tb[i] : 0.0) - ref_b);
+        if (d < lo) { lo = d; ilo = i; }
+        if (d > hi) { hi = d; ihi = i; }
+    }
+    s_lo[threadIdx.x] = lo; s_hi[threadIdx.x] = hi;
+    s_ilo[threadIdx.x] = ilo; s_ihi[threadIdx.x] = ihi;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            if (s_lo[threadIdx.x + w] < s_lo[threadIdx.x]) {
+                s_lo[threadIdx.x] = s_lo[threadIdx.x + w];
+                s_ilo[threadIdx.x] = s_ilo[threadIdx.x + w];
+            }
+            if (s_hi[threadIdx.x + w] > s_hi[threadIdx.x]) {
+                s_hi[threadIdx.x] = s_hi[threadIdx.x + w];
+                s_ihi[threadIdx.x] = s_ihi[threadIdx.x + w];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        range[0] = ta[s_ilo[0]];
+        range[1] = use_jd ? tb[s_ilo[0]] : 0.0;
+        range[2] = ta[s_ihi[0]];
+        range[3] = use_jd ? tb[s_ihi[0]] : 0.0;
+    }
+}
+
+// Pre-pass 2: one thread per resonant satellite walks the +-720 min integrator from epoch
+// across the step indices the grid will need and tabulates (xli, xni) at each node, so that
+// every (satellite, time) evaluation costs O(1) instead of |t|/720 integrator steps. The walk
+// is inherently serial per satellite but short (14 nodes per week of grid).
+__global__ void __launch_bounds__(128)
+resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_t *__restrict__ perm,
+                       size_t first_slot, int n_slots, int first_r2_slot_rel,
+                       const double *__restrict__ range, int use_jd, int cap,
+                       double2 *__restrict__ nodes, int *__restrict__ k0_out,
+                       int *__restrict__ cnt_out) {
+    const int rs = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rs >= n_slots) return;
+    const size_t slot = first_slot + rs;
+    if (perm[slot] < 0) {
+        k0_out[rs] = 0;
+        cnt_out[rs] = 0;
+        return;
+    }
+    const GlobalConsts k = {pf + slot, n_pad};
+    const int irez = (rs >= first_r2_slot_rel) ? 2 : 1;
+    const double t_a = tsince_of(use_jd, range[0], range[1], k(PF_JD0), k(PF_JDF0));
+    const double t_b = tsince_of(use_jd, range[2], range[3], k(PF_JD0), k(PF_JDF0));
+    const int n_a = resonance_step_count(t_a), n_b = resonance_step_count(t_b);
+    int k_lo = (t_a > 0.0) ? n_a : -n_a;
+    int k_hi = (t_b > 0.0) ? n_b : -n_b;
+    if (k_lo > k_hi) { const int tmp = k_lo; k_lo = k_hi; k_hi = tmp; }
+    const int kMaxWalk = 1 << 16;  // ~90 years of 720-minute steps
+    int count = k_hi - k_lo + 1;
+    if (count > cap) count = cap;
+    if (k_lo < -kMaxWalk || k_hi > kMaxWalk) count = 0;  // evaluations fall back to in-line steps
+    k0_out[rs] = k_lo;
+    cnt_out[rs] = count;
+    if (count <= 0) return;
+    const int k_end = k_lo + count;  // tabulate [k_lo, k_end)
+    const size_t stride = static_cast<size_t>(n_slots);
+    const double no = k(PF_NO), xlamo = k(PF_XLAMO);
+    // forwards from epoch
+    if (k_end > 0) {
+        double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
+        for (int kk = 0; kk < k_end; ++kk) {
+            if (kk >= k_lo) nodes[static_cast<size_t>(kk - k_lo) * stride + rs] = make_double2(xli, xni);
+            resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            resonance_advance(xndt, xldot, xnddt, 720.0, xli, xni, atime);
+        }
+    }
+    // backwards from epoch
+    if (k_lo < 0) {
+        double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
+        for (int kk = 0; kk >= k_lo; --kk) {
+            if (kk < k_end && kk <= 0 && !(kk == 0 && k_end > 0)) {
+                nodes[static_cast<size_t>(kk - k_lo) * stride + rs] = make_double2(xli, xni);
+            }
+            resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            resonance_advance(xndt, xldot, xnddt, -720.0, xli, xni, atime);
+        }
+    }
+}
+
 template <int CLS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR : PB_MIN_BLOCKS_DEEP)
 sgp4_prop_kernel(const PropParams p) {
     using TF = TileFields<CLS>;
     __shared__ double s_pf[TF::kRows * PB_TILE_SATS];
     __shared__ double s_ta[kTimeTile];
     __shared__ double s_tb[kTimeTile];
     __shared__ int s_perm[PB_TILE_SATS];
+    constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
+    __shared__ int s_k0[kResonant ? PB_TILE_SATS : 1];
+    __shared__ int s_cnt[kResonant ? PB_TILE_SATS : 1];
 
     const int ttile = blockIdx.x % p.n_time_tiles;
     const int stile = p.tile_begin + blockIdx.x / p.n_time_tiles;
@@ -89,6 +221,12 @@ sgp4_prop_kernel(const PropParams p) {
         s_pf[r * PB_TILE_SATS + lane] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + lane];
     }
     if (threadIdx.x < PB_TILE_SATS) s_perm[threadIdx.x] = p.perm[sat0 + threadIdx.x];
+    if (kResonant && threadIdx.x < PB_TILE_SATS) {
+        const size_t rs = sat0 + threadIdx.x - p.res_first_slot;
+        const bool have = p.res_nodes != nullptr;
+        s_k0[threadIdx.x] = have ? p.res_k0[rs] : 0;
+        s_cnt[threadIdx.x] = have ? p.res_cnt[rs] : 0;
+    }
     const int k_base = ttile * kTimeTile;
     for (int i = threadIdx.x; i < kTimeTile; i += kThreads) {
         // Lanes past the end of the grid re-evaluate the last time (never stored): a made-up
@@ -116,24 +254,39 @@ sgp4_prop_kernel(const PropParams p) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
         const SmemConsts<CLS> k = {s_pf + s};
+        ResNodes nodes = {nullptr, 0, 0, 0};
+        if (kResonant) {
+            nodes.base = p.res_nodes + (sat0 + s - p.res_first_slot);
+            nodes.stride = p.res_stride;
+            nodes.k0 = s_k0[s];
+            nodes.count = s_cnt[s];
+        }
 
         double res[kTpl][6];
         int code[kTpl];
-#pragma unroll
+        // The two evaluations share ONE copy of the code (the body is ~30 KB of SASS and the
+        // instruction cache is 32 KB): a rolled loop whose first result is parked in registers.
+#pragma unroll 1
         for (int j = 0; j < kTpl; ++j) {
             // Satellite::propagate: tsince = ((jd - jd0) + (frac - frac0)) * 1440, grouping
             // as JulianDate::operator- has it (src/perturb.cpp:80-83, 237-238).
-            double t;
-            if (p.use_jd) {
-                const double d = __dadd_rn(__dsub_rn(ta[j], k(PF_JD0)), __dsub_rn(tb[j], k(PF_JDF0)));
-                t = __dmul_rn(d, 1440.0);
-            } else {
-                t = ta[j];
-            }
-            code[j] = sgp4_eval<CLS, false>(k, p.g, p.opsmode_a != 0, no_flags, t, res[j], nullptr);
-            if (code[j] != 0 && code[j] != 6) {
+            const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[1], (j == 0) ? tb[0] : tb[1],
+                                       k(PF_JD0), k(PF_JDF0));
+            double r[6];
+            int cd = sgp4_eval<CLS, false>(k, p.g, p.opsmode_a != 0, no_flags, t, r, nullptr,
+                                           kResonant ? &nodes : nullptr);
+            if (cd != 0 && cd != 6) {
 #pragma unroll
-                for (int c = 0; c < 6; ++c) res[j][c] = nan;
+                for (int c = 0; c < 6; ++c) r[c] = nan;
+            }
+            if (j == 0) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) res[0][c] = r[c];
+                code[0] = cd;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) res[1][c] = r[c];
+                code[1] = cd;
             }
         }
 
@@ -162,14 +315,26 @@ sgp4_prop_kernel(const PropParams p) {
     }
 }
 
+// Classes are independent, so their launches go to forked streams: the small classes fill
+// the tail of the large one instead of running after it.
 template <int CLS>
-void launch_class(const PropLaunch &l, PropParams p, cudaStream_t stream, int &launches) {
+void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &launches) {
     const int tiles = l.tile_count[CLS];
     if (tiles <= 0) return;
     p.tile_begin = l.tile_begin[CLS];
     const long long blocks = static_cast<long long>(tiles) * p.n_time_tiles;
     // grid.x limit is 2^31-1; at 1M satellites x 10k times this is 31250 * 40 blocks.
+    cudaStream_t stream = main;
+    const bool forked = (launches > 0) && l.aux[CLS] != nullptr && l.fork != nullptr;
+    if (forked) {
+        stream = l.aux[CLS];
+        cudaStreamWaitEvent(stream, l.fork, 0);
+    }
     sgp4_prop_kernel<CLS><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    if (forked) {
+        cudaEventRecord(l.join[CLS], stream);
+        cudaStreamWaitEvent(main, l.join[CLS], 0);
+    }
     ++launches;
 }
 
@@ -200,14 +365,39 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.g.j2 = l.j2;
     p.g.j3oj2 = l.j3oj2;
     p.g.vkmpersec = l.radiusearthkm * l.xke / 60.0;
+    p.g.inv_xke = 1.0 / l.xke;
     p.opsmode_a = l.opsmode_a;
     int launches = 0;
+    p.res_nodes = nullptr;
+    p.res_k0 = p.res_cnt = nullptr;
+    p.res_stride = 0;
+    p.res_first_slot = 0;
+    const int res_tiles = l.tile_count[PB_CLS_DEEP_R1] + l.tile_count[PB_CLS_DEEP_R2];
+    if (res_tiles > 0 && l.res_nodes != nullptr && l.res_cap > 0) {
+        const int n_slots = res_tiles * PB_TILE_SATS;
+        const size_t first_slot = static_cast<size_t>(l.tile_begin[PB_CLS_DEEP_R1]) * PB_TILE_SATS;
+        time_range_kernel<<<1, 256, 0, stream>>>(l.ta, l.tb, l.m, l.use_jd, l.res_range);
+        resonance_nodes_kernel<<<(n_slots + 127) / 128, 128, 0, stream>>>(
+            l.pf, l.n_pad, l.perm, first_slot, n_slots,
+            l.tile_count[PB_CLS_DEEP_R1] * PB_TILE_SATS, l.res_range, l.use_jd, l.res_cap,
+            l.res_nodes, l.res_k0, l.res_cnt);
+        launches += 2;
+        p.res_nodes = l.res_nodes;
+        p.res_k0 = l.res_k0;
+        p.res_cnt = l.res_cnt;
+        p.res_stride = static_cast<size_t>(n_slots);
+        p.res_first_slot = first_slot;
+    }
+    const int prelaunches = launches;
+    launches = 0;
+    if (l.fork != nullptr) cudaEventRecord(l.fork, stream);
+    // most expensive per evaluation first
+    launch_class<PB_CLS_DEEP_R2>(l, p, stream, launches);
+    launch_class<PB_CLS_DEEP_R1>(l, p, stream, launches);
+    launch_class<PB_CLS_DEEP_NR>(l, p, stream, launches);
     launch_class<PB_CLS_NEAR_FULL>(l, p, stream, launches);
     launch_class<PB_CLS_NEAR_SIMP>(l, p, stream, launches);
-    launch_class<PB_CLS_DEEP_NR>(l, p, stream, launches);
-    launch_class<PB_CLS_DEEP_R1>(l, p, stream, launches);
-    launch_class<PB_CLS_DEEP_R2>(l, p, stream, launches);
-    return launches;
+    return launches + prelaunches;
 }
 
 }  // namespace pb

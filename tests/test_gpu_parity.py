@@ -46,10 +46,11 @@ def test_verification_catalogue_init(ops):
             continue
         # computed fields: libdevice vs glibc may differ in the last ulps; 1 - cos^2 style
         # cancellations (x1mth2 at i = 0.002 deg) amplify that, hence the absolute floor.
-        scale = np.maximum(np.abs(want), 1.0e-6)
-        rel = np.abs(got - want) / scale
-        assert rel.max() < 1.0e-11, (name, rel.max(), rel.argmax())
-        worst = max(worst, rel.max())
+        excess = np.abs(got - want) - (1.0e-11 * np.abs(want) + 1.0e-14)
+        assert excess.max() <= 0.0, (name, excess.max(), excess.argmax())
+        big = np.abs(want) > 1.0e-3
+        if big.any():
+            worst = max(worst, (np.abs(got - want)[big] / np.abs(want)[big]).max())
     print("worst relative record difference %.2e" % worst)
 
 
@@ -203,6 +204,40 @@ def test_other_gravity_models(grav):
     compare_states(err, pos, vel, eo, ro, vo, sr, sv, "gravity model %d" % grav)
 
 
+def test_resonant_node_table_long_negative_and_unsorted_spans():
+    """Deep-space resonant satellites over grids that (a) straddle the epoch, (b) exceed the
+    64-node table (in-line fall-back), (c) are not sorted in time."""
+    n = 600
+    b1, b2 = pb.synth_catalog(4, n, seed=21)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, "i", flavor=1)
+    assert set(np.unique(b.orbit_class())) == {3, 4}
+    rng = np.random.default_rng(8)
+    grids = {
+        "straddle": np.linspace(-3.0 * 1440, 4.0 * 1440, 141),
+        "long": np.linspace(-20.0 * 1440, 70.0 * 1440, 181),
+        "shuffled": rng.permutation(np.linspace(-2000.0, 9000.0, 97)),
+        "node edges": np.array([-1440.0, -720.0, -719.999999, 0.0, 719.999999, 720.0, 1440.0,
+                                720.0 * 5, np.nextafter(720.0 * 5, 0.0)]),
+    }
+    for name, mins in grids.items():
+        pv, err = b.propagate_from_epoch(mins)
+        pos, vel = posvel_to_rv(pv)
+        eo, ro, vo, _ = orc.propagate_grid(np.sort(mins), nthreads=8)
+        order = np.argsort(mins, kind="stable")
+        sr, sv = oracle_sensitivity_mins(orc, np.sort(mins))
+        stats = compare_states(err[:, order], pos[:, order], vel[:, order], eo, ro, vo, sr, sv,
+                               "resonant " + name)
+        print(name, stats)
+    # the table is an optimisation only: a sub-grid gives the same bits as the full grid
+    mins = grids["long"]
+    full, efull = b.propagate_from_epoch(mins)
+    part, epart = b.propagate_from_epoch(mins[100:140])
+    assert np.array_equal(full[:, :, 100:140], part, equal_nan=True)
+    assert np.array_equal(efull[:, 100:140], epart)
+
+
 # ---- structural properties (bit-exact, size independent) ---------------------------------
 def _mixed_batch(n=3000, seed=5):
     b1, b2 = pb.synth_catalog(3, n, seed=seed)
@@ -267,7 +302,7 @@ def test_device_resident_buffers():
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), host, equal_nan=True)
     assert np.array_equal(err.cpu().numpy(), ehost)
-    assert b.last_launch_count() >= 4  # one launch per non-empty orbit class
+    assert b.last_launch_count() >= 5  # one launch per non-empty orbit class + node table
 
 
 def test_edge_cases_empty_single_and_tile_boundaries():
