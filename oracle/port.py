@@ -20,12 +20,13 @@ _DBL_FIELDS = (
     "sl2 sl3 sl4 gsto xfact xgh2 xgh3 xgh4 xh2 xh3 xi2 xi3 xl2 xl3 xl4 xlamo zmol zmos "
     "atime xli xni "
     "a altp alta jdsatepoch jdsatepochF nddot ndot bstar inclo nodeo ecco argpo mo no_kozai "
-    "no_unkozai am em im Om om mm nm tumin mus radiusearthkm xke j2 j3 j4 j3oj2"
+    "no_unkozai am em im Om om mm nm tumin mus radiusearthkm xke j2 j3 j4 j3oj2 kepler_last cond"
 ).split()
 
 
 class OrcSat(C.Structure):
-    _fields_ = [(n, C.c_int) for n in _INT_FIELDS] + [(n, C.c_double) for n in _DBL_FIELDS]
+    _fields_ = ([(n, C.c_int) for n in _INT_FIELDS] + [(n, C.c_double) for n in _DBL_FIELDS]
+                + [("kepler_iters", C.c_int), ("pad_", C.c_int)])
 
 
 class OrcTle(C.Structure):
@@ -65,6 +66,9 @@ def lib():
         L.orc_propagate_grid.argtypes = [
             C.POINTER(OrcSat), C.c_long, dp, dp, C.c_long, C.c_int, C.c_int, dp, dp,
             C.POINTER(C.c_int)]
+        L.orc_propagate_grid_diag.restype = C.c_double
+        L.orc_propagate_grid_diag.argtypes = L.orc_propagate_grid.argtypes + [
+            C.POINTER(C.c_ubyte), dp]
         L.orc_gstime.restype = C.c_double
         L.orc_gstime.argtypes = [C.c_double]
         _lib = L
@@ -94,14 +98,32 @@ class OracleSatellites:
         for i, (a, b) in enumerate(zip(lines1, lines2)):
             self.parse_error[i] = L.orc_parse_tle(
                 a.encode(), b.encode(), flavor, C.byref(self.tles[i]))
-            if flavor == 1:
-                L.orc_sat_from_vallado_fields(
-                    C.byref(self.sats[i]), C.byref(self.tles[i]), grav, opsmode.encode())
-            else:
-                L.orc_sat_from_tle(
-                    C.byref(self.sats[i]), C.byref(self.tles[i]), grav, opsmode.encode())
-            self.init_error[i] = self.sats[i].error
+        self._init_from_tles(grav, opsmode, flavor)
         return self
+
+    def _init_from_tles(self, grav, opsmode, flavor):
+        L = lib()
+        self.grav, self.opsmode, self.flavor = grav, opsmode, flavor
+        fn = L.orc_sat_from_vallado_fields if flavor == 1 else L.orc_sat_from_tle
+        for i in range(self.n):
+            fn(C.byref(self.sats[i]), C.byref(self.tles[i]), grav, opsmode.encode())
+            self.init_error[i] = self.sats[i].error
+
+    def perturbed(self, sign=+1):
+        """A copy whose orbital elements are moved by one ulp each (alternating directions):
+        the conditioning probe of tests/helpers.py."""
+        other = OracleSatellites(self.n)
+        other.tles = (OrcTle * self.n)()
+        names = ("mean_motion eccentricity inclination raan arg_of_perigee mean_anomaly "
+                 "b_star").split()
+        for i in range(self.n):
+            C.memmove(C.byref(other.tles[i]), C.byref(self.tles[i]), C.sizeof(OrcTle))
+            for j, nm in enumerate(names):
+                v = getattr(other.tles[i], nm)
+                d = sign * (1.0 if j % 2 == 0 else -1.0)
+                setattr(other.tles[i], nm, float(np.nextafter(v, v + d * (abs(v) + 1.0))))
+        other._init_from_tles(self.grav, self.opsmode, self.flavor)
+        return other
 
     @classmethod
     def from_raw(cls, el, grav=1, opsmode="i"):
@@ -150,7 +172,10 @@ class OracleSatellites:
         else:
             pos = vel = None
             pp = vp = None
-        secs = lib().orc_propagate_grid(
+        self.converged = np.ones((self.n, m), dtype=np.uint8)
+        self.cond = np.zeros((self.n, m))
+        secs = lib().orc_propagate_grid_diag(
             self.sats, self.n, _dp(ta), _dp(tb), m, int(bool(use_jd)), int(nthreads), pp, vp,
-            err.ctypes.data_as(C.POINTER(C.c_int)))
+            err.ctypes.data_as(C.POINTER(C.c_int)),
+            self.converged.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(self.cond))
         return err, pos, vel, secs

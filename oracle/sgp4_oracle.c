@@ -663,12 +663,15 @@ int orc_sgp4(orc_sat *s, double tsince, double r[3], double v[3]) {
         eo1 = eo1 + tem5;
         ktr = ktr + 1;
     }
+    s->kepler_iters = ktr - 1;
+    s->kepler_last = tem5;
 
     /* short-period preliminaries, :1986-2011 */
     const double ecose = axnl * coseo1 + aynl * sineo1;
     const double esine = axnl * sineo1 - aynl * coseo1;
     const double el2 = axnl * axnl + aynl * aynl;
     const double pl = am * (1.0 - el2);
+    s->cond = am / pl;
     if (pl < 0.0) {
         s->error = 4;
         return 0;
@@ -1027,6 +1030,8 @@ typedef struct {
     int use_jd;
     double *pos, *vel;
     int *err;
+    unsigned char *converged;
+    double *cond;
 } grid_job;
 
 static void *grid_worker(void *arg) {
@@ -1034,6 +1039,9 @@ static void *grid_worker(void *arg) {
     for (long i = j->lo; i < j->hi; ++i) {
         orc_sat s = j->sats[i];
         for (long k = 0; k < j->m; ++k) {
+            s.kepler_iters = 0;
+            s.kepler_last = 0.0;
+            s.cond = 0.0;
             double r[3] = {NAN, NAN, NAN}, v[3] = {NAN, NAN, NAN};
             int e;
             if (j->use_jd)
@@ -1048,6 +1056,9 @@ static void *grid_worker(void *arg) {
                 }
             }
             if (j->err) j->err[o] = e;
+            if (j->converged)
+                j->converged[o] = !(s.kepler_iters >= 10 && fabs(s.kepler_last) >= 1.0e-12);
+            if (j->cond) j->cond[o] = s.cond;
         }
     }
     return NULL;
@@ -1055,6 +1066,13 @@ static void *grid_worker(void *arg) {
 
 double orc_propagate_grid(const orc_sat *sats, long n, const double *ta, const double *tb,
                           long m, int use_jd, int nthreads, double *pos, double *vel, int *err) {
+    return orc_propagate_grid_diag(sats, n, ta, tb, m, use_jd, nthreads, pos, vel, err, NULL,
+                                   NULL);
+}
+
+double orc_propagate_grid_diag(const orc_sat *sats, long n, const double *ta, const double *tb,
+                               long m, int use_jd, int nthreads, double *pos, double *vel,
+                               int *err, unsigned char *converged, double *cond) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 1024) nthreads = 1024;
     struct timespec t0, t1;
@@ -1062,7 +1080,8 @@ double orc_propagate_grid(const orc_sat *sats, long n, const double *ta, const d
     pthread_t th[1024];
     grid_job jobs[1024];
     for (int t = 0; t < nthreads; ++t) {
-        grid_job j = {sats, n * t / nthreads, n * (t + 1) / nthreads, m, ta, tb, use_jd, pos, vel, err};
+        grid_job j = {sats, n * t / nthreads, n * (t + 1) / nthreads, m, ta, tb, use_jd, pos, vel, err,
+                      converged, cond};
         jobs[t] = j;
         if (nthreads == 1)
             grid_worker(&jobs[t]);

@@ -46,6 +46,13 @@ typedef struct orc_sat {
         argpo, mo, no_kozai, no_unkozai;
     double am, em, im, Om, om, mm, nm;
     double tumin, mus, radiusearthkm, xke, j2, j3, j4, j3oj2;
+    /* diagnostics of the last orc_sgp4 call (not part of elsetrec): Kepler iterations done and
+     * the last Newton correction. kepler_iters == 10 with |kepler_last| >= 1e-12 means the
+     * reference's loop (src/sgp4.cpp:1973-1983) ran out of iterations without converging: the
+     * state it then returns is a function of rounding noise, not of the orbit. */
+    double kepler_last;
+    double cond; /* am / pl = 1 / (1 - el2): how much the short-period step amplifies rounding */
+    int kepler_iters, pad_;
 } orc_sat;
 
 /* getgravconst, src/sgp4.cpp:2101-2157 */
@@ -86,6 +93,11 @@ int orc_parse_tle(const char *line1, const char *line2, int flavor, orc_tle *out
  * slices over nthreads. Returns wall seconds. */
 double orc_propagate_grid(const orc_sat *sats, long n, const double *ta, const double *tb,
                           long m, int use_jd, int nthreads, double *pos, double *vel, int *err);
+/* Same, and also reports per evaluation whether Kepler's equation converged (1) or the loop
+ * ran out of iterations (0), and the conditioning figure `cond`; both [n][m], may be NULL. */
+double orc_propagate_grid_diag(const orc_sat *sats, long n, const double *ta, const double *tb,
+                               long m, int use_jd, int nthreads, double *pos, double *vel,
+                               int *err, unsigned char *converged, double *cond);
 
 int orc_sizeof_sat(void);
 

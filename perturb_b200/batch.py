@@ -196,8 +196,12 @@ class SatelliteBatch:
             s = [x // es for x in posvel.strides]
         else:
             s = list(posvel.stride())
-        assert s[2] == 1, "time must be the contiguous axis"
-        return s[1], s[0]  # row_stride, plane_stride (doubles)
+        if n == 0 or m == 0:
+            return max(m, 1), max(n * m, 1)
+        assert s[2] == 1 or m == 1, "time must be the contiguous axis"
+        row = s[1] if n > 1 else max(m, s[1] if s[1] >= m else m)
+        plane = s[0]
+        return row, max(plane, n * row)  # row_stride, plane_stride (doubles)
 
     def propagate(self, jd, jd_frac, posvel=None, err=None, stream=None, sync=True):
         """All satellites x all JulianDate(jd[k], jd_frac[k]).

@@ -10,10 +10,14 @@ GOLDEN = os.path.join(HERE, "golden")
 # 1e-6 km and velocity within 1e-9 km/s.
 TOL_POS_KM = 1.0e-6
 TOL_VEL_KMS = 1.0e-9
-# An evaluation whose ORACLE output moves by `s` when its input time moves by one ulp is
-# ill-conditioned (decayed / e -> 1 garbage states reach 1e7 km): no implementation with a
-# different libm can hold an absolute bound there, so the bound is widened by SENS_GAIN * s.
-SENS_GAIN = 1.0e4
+# Conditioning: some orbits are numerically ill-posed for ANY implementation -- e.g. a GTO
+# whose perigee touches the Earth has eta -> 1, so cc1 ~ (1 - eta^2)^-3.5 turns a 1-ulp
+# difference of libm's pow() at initialisation into 1e-12 relative, which then grows like t^2;
+# decayed "garbage" states reach 1e7 km. To tell those from real disagreement the oracle is
+# re-run with every orbital element moved by ONE ulp: `s` = how far its own answer moves.
+# Healthy evaluations have s ~ 1e-11..1e-9 km. The bar is widened by SENS_GAIN * s, and
+# "regular" evaluations (widening below the bar itself) are reported separately.
+SENS_GAIN = 64.0
 
 ISS_1 = "1 25544U 98067A   22071.78032407  .00021395  00000-0  39008-3 0  9996"
 ISS_2 = "2 25544  51.6424  94.0370 0004047 256.5103  89.8846 15.49386383330227"
@@ -33,32 +37,30 @@ def ver_lines(g, cols=69):
     return l1, l2
 
 
-def oracle_sensitivity_mins(orc, mins):
-    """max |state(t) - state(t +- few ulp)| of the oracle, per (sat, time)."""
-    mins = np.asarray(mins, dtype=np.float64)
-    e0, r0, v0, _ = orc.propagate_grid(mins)
+def _sensitivity(orc, ta, tb, use_jd):
+    e0, r0, v0, _ = orc.propagate_grid(ta, tb, use_jd=use_jd, nthreads=8)
     sr = np.zeros(e0.shape)
     sv = np.zeros(e0.shape)
-    for sgn in (+1.0, -1.0):
-        tp = mins + sgn * 4.0 * np.spacing(np.maximum(np.abs(mins), 1.0))
-        _, r1, v1, _ = orc.propagate_grid(tp)
-        sr = np.fmax(sr, np.nan_to_num(np.abs(r1 - r0).max(-1), nan=0.0, posinf=1e300))
-        sv = np.fmax(sv, np.nan_to_num(np.abs(v1 - v0).max(-1), nan=0.0, posinf=1e300))
-    return sr, sv
+    for sign in (+1, -1):
+        e1, r1, v1, _ = orc.perturbed(sign).propagate_grid(ta, tb, use_jd=use_jd, nthreads=8)
+        dr = np.abs(r1 - r0).max(-1)
+        dv = np.abs(v1 - v0).max(-1)
+        # a code flip or NaN under a 1-ulp change of the elements: as ill-conditioned as it gets
+        wild = (e1 != e0) | ~np.isfinite(dr) | ~np.isfinite(dv)
+        sr = np.fmax(sr, np.where(wild, 1e300, dr))
+        sv = np.fmax(sv, np.where(wild, 1e300, dv))
+    written = (e0 == 0) | (e0 == 6)
+    return np.where(written, sr, 0.0), np.where(written, sv, 0.0)
+
+
+def oracle_sensitivity_mins(orc, mins):
+    """Per (sat, time): how far the oracle's own state moves under 1-ulp element changes."""
+    return _sensitivity(orc, np.asarray(mins, dtype=np.float64), None, False)
 
 
 def oracle_sensitivity_jd(orc, jd, fr):
-    jd = np.asarray(jd, dtype=np.float64)
-    fr = np.asarray(fr, dtype=np.float64)
-    e0, r0, v0, _ = orc.propagate_grid(jd, fr, use_jd=True)
-    sr = np.zeros(e0.shape)
-    sv = np.zeros(e0.shape)
-    for sgn in (+1.0, -1.0):
-        fp = fr + sgn * 1.0e-12  # ~1e-9 min: a few ulp of a multi-day tsince
-        _, r1, v1, _ = orc.propagate_grid(jd, fp, use_jd=True)
-        sr = np.fmax(sr, np.nan_to_num(np.abs(r1 - r0).max(-1), nan=0.0, posinf=1e300))
-        sv = np.fmax(sv, np.nan_to_num(np.abs(v1 - v0).max(-1), nan=0.0, posinf=1e300))
-    return sr, sv
+    return _sensitivity(orc, np.asarray(jd, dtype=np.float64), np.asarray(fr, dtype=np.float64),
+                        True)
 
 
 def compare_states(err, pos, vel, ref_err, ref_pos, ref_vel, sens_r=None, sens_v=None,
@@ -86,7 +88,7 @@ def compare_states(err, pos, vel, ref_err, ref_pos, ref_vel, sens_r=None, sens_v
         what, dr[bad_r].max(), tol_r[bad_r][dr[bad_r].argmax()], np.argwhere(bad_r)[0])
     assert not bad_v.any(), "%s: |dv| %.3e km/s > tol %.3e at %s" % (
         what, dv[bad_v].max(), tol_v[bad_v][dv[bad_v].argmax()], np.argwhere(bad_v)[0])
-    regular = written & (tol_r <= 2 * TOL_POS_KM)
+    regular = written & (tol_r <= 2 * TOL_POS_KM) & (tol_v <= 2 * TOL_VEL_KMS)
     return {
         "evals": int(err.size),
         "regular": int(regular.sum()),
