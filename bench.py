@@ -117,9 +117,9 @@ def catalogue_lines(workload, rank, world):
     cfg, n, m = WORKLOADS[workload]
     total = n * world
     b1, b2 = pb.synth_catalog(cfg, total)
-    s = pb.capi.SYNTH_LINE_STRIDE
-    lo, hi = rank * n, (rank + 1) * n
-    return b1[lo * s: hi * s], b2[lo * s: hi * s], n, m
+    s1, s2, n_local = pb.shard_blocks(b1, b2, total, rank, world)
+    assert n_local == n
+    return s1, s2, n, m
 
 
 def cpu_arm(workload, steps, warmup, cores=None, budget_s=12.0):
@@ -264,10 +264,7 @@ def run_gpu(args):
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
+    max_ms = pb.max_over_ranks(total_ms, dist, dev)
     evals_step_rank = float(n) * m
     value = evals_step_rank * world * args.steps / (max_ms * 1e-3)
 
@@ -298,10 +295,7 @@ def run_gpu(args):
         batch.propagate(h_jd, h_fr, h_out, h_err)  # synchronises: results are on the host
         _ = int(h_err[0, 0])
     e2e_s = time.perf_counter() - te
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = evals_step_rank * world * e2e_steps / float(t.item())
+    e2e_value = evals_step_rank * world * e2e_steps / pb.max_over_ranks(e2e_s, dist, dev)
     codes_ok = float((h_err == 0).double().mean())
 
     if rank != 0:
