@@ -471,14 +471,16 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     size_t free_b = 0, total_b = 0;
     PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t bytes_per_eval = 6 * sizeof(double) + sizeof(int32_t);
-    size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(2) << 30);  // per buffer
+    size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(8) << 30);  // per buffer
     for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * bytes_per_eval);
-    size_t mc = budget / (bytes_per_eval * b->n);
-    mc = std::min(mc, m);
-    mc &= ~static_cast<size_t>(1);  // even: keeps 16 B store alignment
-    if (mc < 2) mc = std::min<size_t>(m, 2);
-    const size_t mc_pad = (mc + 1) & ~static_cast<size_t>(1);
-    const size_t nchunks = (m + mc - 1) / mc;
+    const size_t m_even = (m + 1) & ~static_cast<size_t>(1);
+    size_t fit = budget / (bytes_per_eval * b->n);  // times one staging buffer can hold
+    fit &= ~static_cast<size_t>(1);
+    if (fit < 2) fit = 2;
+    // Balanced chunks (not "full, full, ..., sliver"): short rows make poor 2-D copies.
+    const size_t nchunks = (m_even + fit - 1) / fit;
+    size_t mc = ((m + nchunks - 1) / nchunks + 1) & ~static_cast<size_t>(1);  // even
+    const size_t mc_pad = mc;
     const int nbuf = nchunks > 1 ? 2 : 1;
     for (int i = 0; i < nbuf; ++i) {
         int st = ensure_stage(b, i, b->n * mc_pad);
@@ -487,29 +489,51 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     for (size_t c = 0; c < nchunks; ++c) {
         const int buf = static_cast<int>(c % 2);
         const size_t k0 = c * mc;
+        if (k0 >= m) break;
         const size_t mk = std::min(mc, m - k0);
         if (c >= 2) PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[buf], 0));
         l.ta = d_ta + k0;
         l.tb = use_jd ? d_tb + k0 : nullptr;
         l.m = static_cast<int>(mk);
         l.out = b->d_stage[buf];
-        l.row_stride = mc_pad;
-        l.plane_stride = b->n * mc_pad;
+        // one chunk covering whole contiguous caller rows: stage with the caller's own
+        // strides so that the D2H is a single linear copy per buffer
+        const bool linear = (nchunks == 1) && (row_stride == m) && (m % 2 == 0);
+        l.row_stride = linear ? m : mc_pad;
+        l.plane_stride = b->n * l.row_stride;
         l.err = b->d_stage_err[buf];
-        l.err_row_stride = mc_pad;
+        l.err_row_stride = l.row_stride;
         b->last_launches += pb::launch_sgp4_propagate(l, stream);
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaEventRecord(b->ev_done[buf], stream));
         PB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
-        for (int pl = 0; pl < 6; ++pl) {
-            PB_CUDA(cudaMemcpy2DAsync(posvel + pl * plane_stride + k0, row_stride * sizeof(double),
-                                      b->d_stage[buf] + pl * l.plane_stride,
-                                      mc_pad * sizeof(double), mk * sizeof(double), b->n,
-                                      cudaMemcpyDeviceToHost, b->copy_stream));
+        if (linear) {
+            if (plane_stride == b->n * m) {
+                PB_CUDA(cudaMemcpyAsync(posvel, b->d_stage[buf], 6 * b->n * m * sizeof(double),
+                                        cudaMemcpyDeviceToHost, b->copy_stream));
+            } else {
+                for (int pl = 0; pl < 6; ++pl) {
+                    PB_CUDA(cudaMemcpyAsync(posvel + pl * plane_stride,
+                                            b->d_stage[buf] + pl * l.plane_stride,
+                                            b->n * m * sizeof(double), cudaMemcpyDeviceToHost,
+                                            b->copy_stream));
+                }
+            }
+            PB_CUDA(cudaMemcpyAsync(err, b->d_stage_err[buf], b->n * m * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, b->copy_stream));
+        } else {
+            for (int pl = 0; pl < 6; ++pl) {
+                PB_CUDA(cudaMemcpy2DAsync(posvel + pl * plane_stride + k0,
+                                          row_stride * sizeof(double),
+                                          b->d_stage[buf] + pl * l.plane_stride,
+                                          mc_pad * sizeof(double), mk * sizeof(double), b->n,
+                                          cudaMemcpyDeviceToHost, b->copy_stream));
+            }
+            PB_CUDA(cudaMemcpy2DAsync(err + k0, row_stride * sizeof(int32_t),
+                                      b->d_stage_err[buf], mc_pad * sizeof(int32_t),
+                                      mk * sizeof(int32_t), b->n, cudaMemcpyDeviceToHost,
+                                      b->copy_stream));
         }
-        PB_CUDA(cudaMemcpy2DAsync(err + k0, row_stride * sizeof(int32_t), b->d_stage_err[buf],
-                                  mc_pad * sizeof(int32_t), mk * sizeof(int32_t), b->n,
-                                  cudaMemcpyDeviceToHost, b->copy_stream));
         PB_CUDA(cudaEventRecord(b->ev_free[buf], b->copy_stream));
     }
     // The caller's stream must see the copies as part of this call.

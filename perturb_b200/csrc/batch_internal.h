@@ -23,6 +23,10 @@ void launch_sgp4init(const void *d_tles, int n, const GravAll &g, bool opsmode_a
                      double *d_pf_stage, uint8_t *d_cls, int32_t *d_init_error,
                      cudaStream_t stream);
 
+// TLE text -> TleNumbers on the device (one thread per TLE). Lines are fixed-stride records.
+void launch_tle_parse(const char *d_lines1, const char *d_lines2, size_t stride, int n, int flavor,
+                      void *d_tles, int32_t *d_status, cudaStream_t stream);
+
 // Alternate entry: records already initialised (by the caller's own sgp4init); only derives
 // the propagation fields and the class. init_error is taken from rec[RF_error].
 void launch_derive_from_records(int n, const double *d_rec, double *d_pf_stage, uint8_t *d_cls,

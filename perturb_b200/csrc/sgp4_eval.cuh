@@ -358,13 +358,17 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             mp = mp + pl;
             argpp = xls - mp - c0 * nodep;
         }
+        // sin/cos of the perturbed inclination are already known from dpper (s0, c0); the
+        // reference recomputes them after the sign fix (:1950-1951): sin(-x) = -sin(x).
+        sinip = s0;
+        cosip = c0;
         if (xincp < 0.0) {  // :1932
             xincp = -xincp;
             nodep = nodep + kPi;
             argpp = argpp - kPi;
+            sinip = -s0;
         }
         if (ep < 0.0 || ep > 1.0) return 3;  // :1938
-        sincos_cw(wrap_pi2(xincp), sinip, cosip);
         aycof = -0.5 * g.j3oj2 * sinip;
         if (fabs(cosip + 1.0) > 1.5e-12) {
             xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), 1.0 + cosip);
@@ -397,7 +401,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     while (fabs(tem5) >= 1.0e-12 && ktr <= 10) {
         sincos_cw(eo1, sineo1, coseo1);
         tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
-        tem5 = div_fast(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
+        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
         eo1 = eo1 + tem5;
         ktr = ktr + 1;

@@ -75,6 +75,16 @@ __device__ __forceinline__ double rcp_fast(double b) {
     return r;
 }
 
+// a / b to ~2^-40 relative (seed + ONE Newton step, no residual correction). Only for
+// quantities that are themselves Newton corrections, e.g. Kepler's equation: the iteration
+// converges to the same root and its iterates move by < 1e-12 of each correction.
+__device__ __forceinline__ double div_coarse(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = __fma_rn(r, __fma_rn(-b, r, kMc[MC_ONE]), r);
+    return __dmul_rn(a, r);
+}
+
 __device__ __forceinline__ double div_fast(double a, double b) {
     const double r = rcp_fast(b);
     const double q = __dmul_rn(a, r);
@@ -148,23 +158,20 @@ __device__ __forceinline__ double reduce_pio2(double x, int &q) {
     r = __fma_rn(-k, kMc[MC_PIO2_LO], r);
     return r;
 }
-__device__ __forceinline__ double sin_poly(double z) {
-    double p = kMc[MC_S6];
-    p = __fma_rn(p, z, kMc[MC_S5]);
-    p = __fma_rn(p, z, kMc[MC_S4]);
-    p = __fma_rn(p, z, kMc[MC_S3]);
-    p = __fma_rn(p, z, kMc[MC_S2]);
-    p = __fma_rn(p, z, kMc[MC_S1]);
-    return p;
+// Degree-5 polynomials in z evaluated Estrin-style: the same five FMAs as Horner plus the
+// shared z^2, but a dependency depth of 3 instead of 6 -- the kernel is latency-sensitive at
+// 5 warps per scheduler (ncu: "wait" is the top stall reason).
+__device__ __forceinline__ double sin_poly(double z, double zz) {
+    const double a = __fma_rn(kMc[MC_S2], z, kMc[MC_S1]);
+    const double b = __fma_rn(kMc[MC_S4], z, kMc[MC_S3]);
+    const double c = __fma_rn(kMc[MC_S6], z, kMc[MC_S5]);
+    return __fma_rn(__fma_rn(c, zz, b), zz, a);
 }
-__device__ __forceinline__ double cos_poly(double z) {
-    double p = kMc[MC_C6];
-    p = __fma_rn(p, z, kMc[MC_C5]);
-    p = __fma_rn(p, z, kMc[MC_C4]);
-    p = __fma_rn(p, z, kMc[MC_C3]);
-    p = __fma_rn(p, z, kMc[MC_C2]);
-    p = __fma_rn(p, z, kMc[MC_C1]);
-    return p;
+__device__ __forceinline__ double cos_poly(double z, double zz) {
+    const double a = __fma_rn(kMc[MC_C2], z, kMc[MC_C1]);
+    const double b = __fma_rn(kMc[MC_C4], z, kMc[MC_C3]);
+    const double c = __fma_rn(kMc[MC_C6], z, kMc[MC_C5]);
+    return __fma_rn(__fma_rn(c, zz, b), zz, a);
 }
 __device__ __forceinline__ double flip_sign(double v, int neg) {
     // XOR the sign bit: integer pipe, not FP64
@@ -178,8 +185,9 @@ __device__ __forceinline__ void sincos_cw(double x, double &s, double &c) {
     int q;
     const double r = detail::reduce_pio2(x, q);
     const double z = __dmul_rn(r, r);
-    const double sr = __fma_rn(__dmul_rn(r, z), detail::sin_poly(z), r);
-    const double cr = __fma_rn(__dmul_rn(z, z), detail::cos_poly(z),
+    const double zz = __dmul_rn(z, z);
+    const double sr = __fma_rn(__dmul_rn(r, z), detail::sin_poly(z, zz), r);
+    const double cr = __fma_rn(zz, detail::cos_poly(z, zz),
                                __fma_rn(-kMc[MC_HALF], z, kMc[MC_ONE]));
     const bool odd = (q & 1) != 0;
     const double ss = odd ? cr : sr;
@@ -197,15 +205,14 @@ __device__ __forceinline__ double sin_or_cos_cw(double x) {
     if (WANT_COS) q += 1;  // cos(x) = sin(x + pi/2)
     const bool use_cos = (q & 1) != 0;
     const double z = __dmul_rn(r, r);
-    double p = use_cos ? kMc[MC_C6] : kMc[MC_S6];
-    p = __fma_rn(p, z, use_cos ? kMc[MC_C5] : kMc[MC_S5]);
-    p = __fma_rn(p, z, use_cos ? kMc[MC_C4] : kMc[MC_S4]);
-    p = __fma_rn(p, z, use_cos ? kMc[MC_C3] : kMc[MC_S3]);
-    p = __fma_rn(p, z, use_cos ? kMc[MC_C2] : kMc[MC_S2]);
-    p = __fma_rn(p, z, use_cos ? kMc[MC_C1] : kMc[MC_S1]);
+    const double zz = __dmul_rn(z, z);
+    const double a = __fma_rn(use_cos ? kMc[MC_C2] : kMc[MC_S2], z, use_cos ? kMc[MC_C1] : kMc[MC_S1]);
+    const double b = __fma_rn(use_cos ? kMc[MC_C4] : kMc[MC_S4], z, use_cos ? kMc[MC_C3] : kMc[MC_S3]);
+    const double c = __fma_rn(use_cos ? kMc[MC_C6] : kMc[MC_S6], z, use_cos ? kMc[MC_C5] : kMc[MC_S5]);
+    const double p = __fma_rn(__fma_rn(c, zz, b), zz, a);
     // sin: r + (r z) p        cos: (1 - z/2) + (z z) p
     const double lead = use_cos ? __fma_rn(-kMc[MC_HALF], z, kMc[MC_ONE]) : r;
-    const double scale = __dmul_rn(use_cos ? z : r, z);
+    const double scale = use_cos ? zz : __dmul_rn(r, z);
     const double v = __fma_rn(scale, p, lead);
     return detail::flip_sign(v, (q >> 1) & 1);
 }

@@ -52,6 +52,8 @@ def test_division_reciprocal_sqrt():
     b = rng.uniform(0.1, 10.0, N) * 10.0 ** rng.integers(-8, 8, N) * rng.choice([-1.0, 1.0], N)
     assert ulps(probe(4, a, b), a / b).max() <= 1.0
     assert ulps(probe(5, b), 1.0 / b).max() <= 1.5
+    coarse = np.abs(probe(14, a, b) - a / b) / np.abs(a / b)
+    assert coarse.max() < 1.0e-9  # seed + one Newton step; used for Newton corrections only
     p = np.abs(b)
     assert ulps(probe(6, p), np.sqrt(p)).max() <= 1.0
     assert ulps(probe(7, p), 1.0 / np.sqrt(p)).max() <= 2.0
