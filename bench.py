@@ -214,6 +214,11 @@ def run_gpu(args):
     t0 = time.perf_counter()
     batch = pb.SatelliteBatch.from_parsed(tles, pb.WGS72, "i", device=local)
     t_init = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    batch_text = pb.SatelliteBatch.from_text(b1, b2, pb.WGS72, "i", device=local, n=n)
+    t_text = time.perf_counter() - t0
+    assert np.array_equal(batch_text.last_error(), batch.last_error())
+    batch_text.close()
     cls = np.bincount(batch.orbit_class(), minlength=5)
     falg = float(sum(F_ALG[c] * cls[c] for c in range(5)) / max(1, cls.sum()))
 
@@ -376,7 +381,9 @@ def run_gpu(args):
         },
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
-        "init": {"satellites": n, "parse_ms": 1e3 * t_parse, "sgp4init_and_sort_ms": 1e3 * t_init},
+        "init": {"satellites": n, "host_parse_ms": 1e3 * t_parse,
+                 "sgp4init_and_sort_ms": 1e3 * t_init,
+                 "device_parse_sgp4init_sort_ms": 1e3 * t_text},
         "wall_s_timed_region": wall,
         "ok_fraction": codes_ok,
     }

@@ -96,6 +96,16 @@ typedef struct perturb_gpu_batch perturb_gpu_batch; /* opaque */
 int perturb_gpu_init(const perturb_gpu_tle *tles, size_t n, int grav_model, char opsmode,
                      int device, perturb_gpu_batch **out, int32_t *init_error);
 
+/* Replaces n x `Satellite::from_tle(line_1, line_2, grav)` (src/perturb.cpp:189-217) when
+ * flavor = 1, or n x `TwoLineElement::parse` + `Satellite(tle, grav)` when flavor = 0, with the
+ * TLE text parsed ON THE DEVICE (one thread per TLE; same code and therefore same bits as
+ * perturb_gpu_parse_tles). lines1 / lines2: n fixed-stride records (host or device),
+ * >= 69 characters used. parse_status [n] host, may be NULL (see perturb_gpu_parse_tles). */
+int perturb_gpu_init_from_text(const char *lines1, const char *lines2, size_t line_stride,
+                               size_t n, int flavor, int grav_model, char opsmode, int device,
+                               perturb_gpu_batch **out, int32_t *init_error,
+                               int32_t *parse_status);
+
 /* Alternate entry: satellites whose `sgp4::elsetrec` was initialised elsewhere (replaces
  * n x `Satellite(sgp4::elsetrec)`, src/perturb.cpp:133). `records` is field-major
  * [perturb_gpu_record_field_count()][n] doubles (host or device), field order given by

@@ -120,6 +120,28 @@ class SatelliteBatch:
         return self
 
     @classmethod
+    def from_text(cls, lines1, lines2, grav=capi.WGS72, opsmode="i", device=0, flavor=1, n=None):
+        """Like from_tles, but the TLE text is parsed on the device (kernel) instead of the
+        host. lines1/lines2: lists of strings, or fixed-stride byte blocks with `n` given."""
+        if isinstance(lines1, (bytes, bytearray)):
+            b1, b2 = bytes(lines1), bytes(lines2)
+        else:
+            n = len(lines1)
+            b1, b2 = _as_line_block(lines1), _as_line_block(lines2)
+        h = C.c_void_p()
+        init_error = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        ip = C.POINTER(C.c_int32)
+        st = capi.lib().perturb_gpu_init_from_text(
+            b1, b2, capi.SYNTH_LINE_STRIDE, n, int(flavor), int(grav), opsmode.encode(),
+            int(device), C.byref(h), init_error.ctypes.data_as(ip), status.ctypes.data_as(ip))
+        capi.check(st, "perturb_gpu_init_from_text")
+        self = cls(h, n)
+        self._init_error = init_error
+        self.parse_status = status
+        return self
+
+    @classmethod
     def from_records(cls, records, grav=capi.WGS72, opsmode="i", device=0):
         """records: float64 [record_field_count, n], field order = record_field_names()."""
         arr = np.ascontiguousarray(records, dtype=np.float64)

@@ -27,7 +27,7 @@ class Tle(C.Structure):
 
 # Every symbol include/perturb_gpu.h and include/perturb_synth.h declare.
 EXPORTS = (
-    "perturb_gpu_init perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
+    "perturb_gpu_init perturb_gpu_init_from_text perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
     "perturb_gpu_propagate_from_epoch perturb_gpu_synchronize perturb_gpu_size "
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
@@ -56,6 +56,8 @@ def lib():
     L.perturb_gpu_init.argtypes = [
         vp, C.c_size_t, C.c_int, C.c_char, C.c_int, C.POINTER(vp), ip]
     L.perturb_gpu_init_records.argtypes = L.perturb_gpu_init.argtypes
+    L.perturb_gpu_init_from_text.argtypes = [
+        vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_char, C.c_int, C.POINTER(vp), ip, ip]
     L.perturb_gpu_free.argtypes = [vp]
     L.perturb_gpu_free.restype = None
     L.perturb_gpu_propagate.argtypes = [

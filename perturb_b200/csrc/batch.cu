@@ -297,9 +297,19 @@ struct ScratchFree {
     }
 };
 
+struct TextSource {
+    const char *lines1, *lines2;
+    size_t stride;
+    int flavor;
+    int32_t *parse_status;  // host, optional
+};
+
 int init_impl(const void *src, bool from_records, size_t n, int grav_model, char opsmode,
-              int device, perturb_gpu_batch **out, int32_t *init_error) {
-    if (src == nullptr && n > 0) return fail(PERTURB_GPU_ERR_ARG, "input array is null");
+              int device, perturb_gpu_batch **out, int32_t *init_error,
+              const TextSource *text = nullptr) {
+    if (src == nullptr && text == nullptr && n > 0) {
+        return fail(PERTURB_GPU_ERR_ARG, "input array is null");
+    }
     perturb_gpu_batch *b = nullptr;
     int st = create_common(n, grav_model, opsmode, device, out, &b);
     if (st != PERTURB_GPU_OK) return st;
@@ -319,6 +329,7 @@ int init_impl(const void *src, bool from_records, size_t n, int grav_model, char
     if (st != PERTURB_GPU_OK) return st;
 
     ScratchFree scratch;  // [0] input copy, [1] pf staging, [2] cls, [3] err
+    ScratchFree text_scratch;  // [0] lines1, [1] lines2, [2] parse status
     double *d_pf_stage = nullptr;
     uint8_t *d_cls = nullptr;
     int32_t *d_err = nullptr;
@@ -336,6 +347,34 @@ int init_impl(const void *src, bool from_records, size_t n, int grav_model, char
             PB_CUDA(cudaMemcpyAsync(b->d_rec, src, bytes, cudaMemcpyDefault, b->stream));
             pb::launch_derive_from_records(static_cast<int>(n), b->d_rec, d_pf_stage, d_cls,
                                            d_err, b->stream);
+        } else if (text != nullptr) {
+            // TLE text -> numbers on the device, then straight into kernel 1
+            const size_t bytes = n * text->stride;
+            const char *d_l1 = text->lines1, *d_l2 = text->lines2;
+            if (!is_device_pointer(text->lines1)) {
+                PB_CUDA(cudaMalloc(&text_scratch.p[0], bytes));
+                PB_CUDA(cudaMemcpyAsync(text_scratch.p[0], text->lines1, bytes,
+                                        cudaMemcpyHostToDevice, b->stream));
+                d_l1 = static_cast<const char *>(text_scratch.p[0]);
+            }
+            if (!is_device_pointer(text->lines2)) {
+                PB_CUDA(cudaMalloc(&text_scratch.p[1], bytes));
+                PB_CUDA(cudaMemcpyAsync(text_scratch.p[1], text->lines2, bytes,
+                                        cudaMemcpyHostToDevice, b->stream));
+                d_l2 = static_cast<const char *>(text_scratch.p[1]);
+            }
+            PB_CUDA(cudaMalloc(&scratch.p[0], n * sizeof(perturb_gpu_tle)));
+            PB_CUDA(cudaMalloc(&text_scratch.p[2], n * sizeof(int32_t)));
+            int32_t *d_status = static_cast<int32_t *>(text_scratch.p[2]);
+            pb::launch_tle_parse(d_l1, d_l2, text->stride, static_cast<int>(n), text->flavor,
+                                 scratch.p[0], d_status, b->stream);
+            PB_CUDA(cudaGetLastError());
+            if (text->parse_status != nullptr) {
+                PB_CUDA(cudaMemcpyAsync(text->parse_status, d_status, n * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, b->stream));
+            }
+            pb::launch_sgp4init(scratch.p[0], static_cast<int>(n), b->grav, b->opsmode_a,
+                                b->d_rec, d_pf_stage, d_cls, d_err, b->stream);
         } else {
             const void *d_tles = src;
             if (!is_device_pointer(src)) {
@@ -550,6 +589,18 @@ extern "C" {
 int perturb_gpu_init(const perturb_gpu_tle *tles, size_t n, int grav_model, char opsmode,
                      int device, perturb_gpu_batch **out, int32_t *init_error) {
     return init_impl(tles, false, n, grav_model, opsmode, device, out, init_error);
+}
+
+int perturb_gpu_init_from_text(const char *lines1, const char *lines2, size_t line_stride,
+                               size_t n, int flavor, int grav_model, char opsmode, int device,
+                               perturb_gpu_batch **out, int32_t *init_error,
+                               int32_t *parse_status) {
+    if ((n > 0 && (lines1 == nullptr || lines2 == nullptr)) || line_stride < 69 ||
+        (flavor != 0 && flavor != 1)) {
+        return fail(PERTURB_GPU_ERR_ARG, "bad TLE text arguments");
+    }
+    const TextSource text = {lines1, lines2, line_stride, flavor, parse_status};
+    return init_impl(nullptr, false, n, grav_model, opsmode, device, out, init_error, &text);
 }
 
 int perturb_gpu_init_records(const double *records, size_t n, int grav_model, char opsmode,

@@ -238,6 +238,49 @@ def test_resonant_node_table_long_negative_and_unsorted_spans():
     assert np.array_equal(efull[:, 100:140], epart)
 
 
+# ---- N1: TLE text parsed on the device ------------------------------------------------------
+@pytest.mark.parametrize("flavor", [0, 1])
+def test_device_tle_parser_equals_host_parser(flavor):
+    """perturb_gpu_init_from_text: same reader code on the device, so every record field,
+    init error and parse status must equal the host-parsed route bit for bit."""
+    l1, l2 = ver_lines(G)
+    n = 3000
+    b1, b2 = pb.synth_catalog(3, n, seed=77)
+    L1 = l1 + pb.block_to_lines(b1, n)
+    L2 = l2 + pb.block_to_lines(b2, n)
+    # malformed members: short line, broken checksum, missing separator, blank digits
+    L1 += [l1[0][:40], l1[2][:68] + "0", l1[3][:8] + "X" + l1[3][9:], l1[4]]
+    L2 += [l2[0], l2[2], l2[3], l2[4][:26] + "  " + l2[4][28:]]
+    host = pb.SatelliteBatch.from_tles(L1, L2, flavor=flavor)
+    dev = pb.SatelliteBatch.from_text(L1, L2, flavor=flavor)
+    assert np.array_equal(host.parse_status, dev.parse_status)
+    assert np.array_equal(host.last_error(), dev.last_error())
+    assert np.array_equal(host.orbit_class(), dev.orbit_class())
+    assert np.array_equal(host.records(), dev.records(), equal_nan=True)
+    if flavor == 1:
+        assert dev.last_error()[len(l1) + n] == 7  # the short line: INVALID_TLE
+    mins = np.array([0.0, 90.0, 1440.0])
+    pa, ea = host.propagate_from_epoch(mins)
+    pd, ed = dev.propagate_from_epoch(mins)
+    assert np.array_equal(ea, ed) and np.array_equal(pa, pd, equal_nan=True)
+
+
+def test_device_tle_parser_matches_reference_parsers():
+    """Against the reference's own readers (golden): twoline2rv numbers via the record,
+    TwoLineElement::parse statuses."""
+    l1, l2 = ver_lines(G)
+    dev = pb.SatelliteBatch.from_text(l1, l2, pb.WGS72, "i", flavor=1)
+    F = G["pub_fields"]
+    for name in ("bstar", "ecco", "inclo", "nodeo", "argpo", "mo", "no_kozai", "ndot", "nddot",
+                 "jdsatepoch", "jdsatepochF"):
+        assert np.array_equal(dev.record_field(name), F[:, NAMES.index(name)]), name
+    assert np.array_equal(dev.last_error(), G["pub_init_error"])
+    dev0 = pb.SatelliteBatch.from_text(l1, l2, pb.WGS72, "i", flavor=0)
+    ok = G["tle_parse_error"] == 0
+    assert (dev0.parse_status[ok] == 0).all()
+    assert (dev0.parse_status == G["tle_parse_error"]).sum() >= len(l1) - 1
+
+
 # ---- structural properties (bit-exact, size independent) ---------------------------------
 def _mixed_batch(n=3000, seed=5):
     b1, b2 = pb.synth_catalog(3, n, seed=seed)
