@@ -157,10 +157,29 @@ struct ResNodes {
 
 // Returns the raw sgp4 error code (0, 1, 2, 3, 4, 6). out[0..2] = r [km], out[3..5] = v
 // [km/s] are written for codes 0 and 6 only, exactly like the reference.
-template <int CLS, bool WANT_SIDE, class K>
+//
+// UNIFORM = true (kernel 2): every lane of the warp is active and evaluates the same
+// satellite. The function then has NO early returns -- the first failure is latched in `code`
+// and the arithmetic simply carries on with garbage that is never stored -- and Kepler's loop
+// is driven by a warp vote, so control flow stays warp-uniform from entry to exit. That is
+// what lets ptxas keep addresses and FP64 constants on the uniform datapath (LDCU into
+// uniform registers, UR-addressed shared loads): the first version's `return`s made everything
+// after them "divergent" and cost ~75 LDC + ~50 R2UR + ~100 moves per evaluation (ncu source
+// page, profiles/). UNIFORM = false (kernel 1's epoch probe, one thread per satellite) keeps
+// plain early returns.
+template <int CLS, bool WANT_SIDE, bool UNIFORM, class K>
 __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool opsmode_a,
                                          ClassFlags rt, double t, double out[6],
                                          Sgp4Side *side, const ResNodes *nodes = nullptr) {
+    int code = 0;
+#define PB_FAIL_IF(cond, c)              \
+    do {                                 \
+        if (UNIFORM) {                   \
+            if (code == 0 && (cond)) code = (c); \
+        } else if (cond) {               \
+            return (c);                  \
+        }                                \
+    } while (0)
     using T = ClassTraits<CLS>;
     const bool deep = T::kStatic ? T::kDeep : rt.deep;
     const bool simp = T::kStatic ? T::kSimp : rt.isimp;
@@ -245,7 +264,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         }
     }
 
-    if (nm <= 0.0) return 2;  // :1860
+    PB_FAIL_IF(nm <= 0.0, 2);  // :1860
 
     double aobase;
     if (deep && irez != 0) {
@@ -258,7 +277,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double sqrt_am = am * rsqrt_am;
     nm = g.xke * (rsqrt_am * rsqrt_am * rsqrt_am);  // xke / pow(am, 1.5)
     em = em - tempe;
-    if (em >= 1.0 || em < -0.001) return 1;  // :1873
+    PB_FAIL_IF(em >= 1.0 || em < -0.001, 1);  // :1873
     if (em < 1.0e-6) em = 1.0e-6;
     mm = mm + no * templ;
     double xlm = mm + argpm + nodem;
@@ -279,7 +298,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         mm = wrap_pi(xlm - argpm - nodem);
     }
 
-    if (WANT_SIDE) {
+    if (WANT_SIDE && code == 0) {
         side->am = am;
         side->em = em;
         side->im = inclm;
@@ -368,14 +387,14 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             argpp = argpp - kPi;
             sinip = -s0;
         }
-        if (ep < 0.0 || ep > 1.0) return 3;  // :1938
+        PB_FAIL_IF(ep < 0.0 || ep > 1.0, 3);  // :1938
         aycof = -0.5 * g.j3oj2 * sinip;
         if (fabs(cosip + 1.0) > 1.5e-12) {
             xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), 1.0 + cosip);
         } else {
             xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / 1.5e-12;
         }
-        if (WANT_SIDE) {
+        if (WANT_SIDE && code == 0) {
             side->aycof = aycof;
             side->xlcof = xlcof;
             side->stage = 2;
@@ -396,15 +415,29 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double xl = mp + argpp + nodep + temp * xlcof * axnl;
 
     const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
-    double eo1 = u, tem5 = 9999.9, sineo1 = 1.0, coseo1 = 1.0;
-    int ktr = 1;
-    while (fabs(tem5) >= 1.0e-12 && ktr <= 10) {
-        sincos_cw(eo1, sineo1, coseo1);
-        tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
-        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
+    // Newton iteration of the reference: at most 10 corrections, stop after one smaller than
+    // 1e-12, clamp a correction to +-0.95; sin/cos kept are those of the LAST EVALUATED
+    // iterate (the reference uses sineo1/coseo1 from before the final update too).
+    double eo1 = u, sineo1 = 1.0, coseo1 = 1.0;
+    bool active = true;
+#pragma unroll 1
+    for (int ktr = 1; ktr <= 10; ++ktr) {
+        if (UNIFORM) {
+            if (!__any_sync(0xffffffffu, active)) break;
+        } else if (!active) {
+            break;
+        }
+        double sn, cs;
+        sincos_cw(eo1, sn, cs);
+        double tem5 = 1.0 - cs * axnl - sn * aynl;
+        tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
-        eo1 = eo1 + tem5;
-        ktr = ktr + 1;
+        if (active) {  // lanes that already converged keep their state
+            sineo1 = sn;
+            coseo1 = cs;
+            eo1 = eo1 + tem5;
+            active = fabs(tem5) >= 1.0e-12;
+        }
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
@@ -412,7 +445,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double esine = axnl * sineo1 - aynl * coseo1;
     const double el2 = axnl * axnl + aynl * aynl;
     const double pl = am * (1.0 - el2);
-    if (pl < 0.0) return 4;  // :1990
+    PB_FAIL_IF(pl < 0.0, 4);  // :1990
 
     const double rl = am * (1.0 - ecose);
     const double inv_rl = rcp_fast(rl);
@@ -435,7 +468,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         con41 = 3.0 * cosisq - 1.0;
         x1mth2 = 1.0 - cosisq;
         x7thm1 = 7.0 * cosisq - 1.0;
-        if (WANT_SIDE) {
+        if (WANT_SIDE && code == 0) {
             side->con41 = con41;
             side->x1mth2 = x1mth2;
             side->x7thm1 = x7thm1;
@@ -487,7 +520,9 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     out[4] = (mvt * uy + rvdot * vy) * g.vkmpersec;
     out[5] = (mvt * uz + rvdot * vz) * g.vkmpersec;
 
-    return (mrt < 1.0) ? 6 : 0;  // :2056
+    PB_FAIL_IF(mrt < 1.0, 6);  // :2056
+#undef PB_FAIL_IF
+    return code;
 }
 
 }  // namespace pb

@@ -28,7 +28,7 @@ __device__ void epoch_probe(SatRec &rec, const double pf[PF_COUNT], bool opsmode
     fl.irez = static_cast<int>(rec.f[RF_irez]);
     double out[6];
     Sgp4Side side;
-    const int code = sgp4_eval<PB_CLS_RUNTIME, true>(LocalConsts {pf}, g, opsmode_a, fl, 0.0,
+    const int code = sgp4_eval<PB_CLS_RUNTIME, true, false>(LocalConsts {pf}, g, opsmode_a, fl, 0.0,
                                                      out, &side);
     rec.f[RF_error] = code;
     if (side.stage >= 1) {

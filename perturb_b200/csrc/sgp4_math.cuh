@@ -173,9 +173,10 @@ __device__ __forceinline__ double cos_poly(double z, double zz) {
     const double c = __fma_rn(kMc[MC_C6], z, kMc[MC_C5]);
     return __fma_rn(__fma_rn(c, zz, b), zz, a);
 }
-__device__ __forceinline__ double flip_sign(double v, int neg) {
-    // XOR the sign bit: integer pipe, not FP64
-    const int hi = __double2hiint(v) ^ (neg << 31);
+// v with its sign flipped when bit 1 of q is set (quadrants 2 and 3): one shift and one
+// AND-XOR on the high word, integer pipe, not FP64.
+__device__ __forceinline__ double flip_sign_q(double v, int q) {
+    const int hi = __double2hiint(v) ^ ((q << 30) & 0x80000000);
     return __hiloint2double(hi, __double2loint(v));
 }
 }  // namespace detail
@@ -192,8 +193,8 @@ __device__ __forceinline__ void sincos_cw(double x, double &s, double &c) {
     const bool odd = (q & 1) != 0;
     const double ss = odd ? cr : sr;
     const double cc = odd ? sr : cr;
-    s = detail::flip_sign(ss, (q >> 1) & 1);
-    c = detail::flip_sign(cc, ((q + 1) >> 1) & 1);
+    s = detail::flip_sign_q(ss, q);
+    c = detail::flip_sign_q(cc, q + 1);
 }
 
 // One of sin/cos only: which kernel is needed depends on quadrant parity, and both kernels
@@ -214,7 +215,7 @@ __device__ __forceinline__ double sin_or_cos_cw(double x) {
     const double lead = use_cos ? __fma_rn(-kMc[MC_HALF], z, kMc[MC_ONE]) : r;
     const double scale = use_cos ? zz : __dmul_rn(r, z);
     const double v = __fma_rn(scale, p, lead);
-    return detail::flip_sign(v, (q >> 1) & 1);
+    return detail::flip_sign_q(v, q);
 }
 
 __device__ __forceinline__ double sin_cw(double x) { return sin_or_cos_cw<false>(x); }

@@ -7,10 +7,10 @@
 //     (32 consecutive satellites = one 256 B row per field) and staged in shared memory,
 //     and so is the CTA's slice of the time grid;
 //   * inside a warp, lanes are consecutive TIMES of ONE satellite: every class/isimp/irez
-//     branch is warp-uniform, constants are shared-memory broadcasts, and a warp's results
-//     are 512 contiguous bytes per output plane, so stores are full-line, 16 B per lane,
-//     straight into the caller-order row (the sort permutation costs nothing on output);
-//   * each lane evaluates TPL = 2 consecutive times per satellite to form those 16 B stores.
+//     branch is warp-uniform, constants are shared-memory broadcasts, and one evaluation of
+//     a warp yields 256 contiguous bytes per output plane, stored as full sectors straight
+//     into the caller-order row (the sort permutation costs nothing on output);
+//   * each lane evaluates TPL = 2 times per satellite (l and l + 32 of the warp's 64).
 // FP64 pipe bound; no tensor cores (not a contraction).
 #include "batch_internal.h"
 #include "sgp4_eval.cuh"
@@ -23,7 +23,7 @@ namespace {
 // profiles/r1_sweeps.md): near-Earth bodies fit 80 registers with a handful of spills and
 // gain from 24 warps/SM; the deep-space bodies are larger and do best at 4 CTAs (128 regs).
 #ifndef PB_MIN_BLOCKS_NEAR
-#define PB_MIN_BLOCKS_NEAR 6
+#define PB_MIN_BLOCKS_NEAR 5
 #endif
 #ifndef PB_MIN_BLOCKS_DEEP
 #define PB_MIN_BLOCKS_DEEP 4
@@ -75,7 +75,6 @@ struct PropParams {
     size_t plane_stride, row_stride;
     int32_t *err;
     size_t err_row_stride;
-    int vec_ok;
     GravConsts g;
     int opsmode_a;
     // resonance node table (deep-space resonant classes only)
@@ -237,14 +236,16 @@ sgp4_prop_kernel(const PropParams p) {
     }
     __syncthreads();
 
-    const int i0 = (warp * 32 + lane) * kTpl;  // this lane's first time within the tile
-    const int k0 = k_base + i0;                // ... and within the grid
+    // Lane l of warp w owns times w*64 + l and w*64 + 32 + l of the tile: each of the two
+    // evaluations of a warp covers 32 CONSECUTIVE times, so its stores are 256 contiguous
+    // bytes per plane (full sectors) issued right after the evaluation.
+    const int i0 = warp * (32 * kTpl) + lane;
     if (k_base + warp * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
     double ta[kTpl], tb[kTpl];
 #pragma unroll
     for (int j = 0; j < kTpl; ++j) {
-        ta[j] = s_ta[i0 + j];
-        tb[j] = s_tb[i0 + j];
+        ta[j] = s_ta[i0 + 32 * j];
+        tb[j] = s_tb[i0 + 32 * j];
     }
     const ClassFlags no_flags = {false, false, 0};
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -261,62 +262,32 @@ sgp4_prop_kernel(const PropParams p) {
             nodes.k0 = s_k0[s];
             nodes.count = s_cnt[s];
         }
+        double *row = p.out + static_cast<size_t>(dst) * p.row_stride;
+        int32_t *erow = p.err + static_cast<size_t>(dst) * p.err_row_stride;
 
-        double res[kTpl][6];
-        int code[kTpl];
-        // The two evaluations share ONE copy of the code (the body is ~30 KB of SASS and the
-        // instruction cache is 32 KB): a rolled loop whose first result is parked in registers.
+        // The two evaluations share ONE copy of the code (a rolled loop): the body is ~15 KB
+        // of SASS and the instruction cache is 32 KB.
 #pragma unroll 1
         for (int j = 0; j < kTpl; ++j) {
-            // Satellite::propagate: tsince = ((jd - jd0) + (frac - frac0)) * 1440, grouping
-            // as JulianDate::operator- has it (src/perturb.cpp:80-83, 237-238).
             const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[1], (j == 0) ? tb[0] : tb[1],
                                        k(PF_JD0), k(PF_JDF0));
             double r[6];
-            int cd = sgp4_eval<CLS, false>(k, p.g, p.opsmode_a != 0, no_flags, t, r, nullptr,
-                                           kResonant ? &nodes : nullptr);
-            if (cd != 0 && cd != 6) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) r[c] = nan;
-            }
-            if (j == 0) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) res[0][c] = r[c];
-                code[0] = cd;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) res[1][c] = r[c];
-                code[1] = cd;
-            }
-        }
-
-        // ---- stores: caller-order row `dst`, 16 B per lane per plane ----
-        if (k0 < p.m) {
-            double *row = p.out + static_cast<size_t>(dst) * p.row_stride + k0;
-            int32_t *erow = p.err + static_cast<size_t>(dst) * p.err_row_stride + k0;
-            if (p.vec_ok && k0 + 1 < p.m) {
+            const int cd = sgp4_eval<CLS, false, true>(k, p.g, p.opsmode_a != 0, no_flags, t, r,
+                                                       nullptr, kResonant ? &nodes : nullptr);
+            const int kt = k_base + i0 + 32 * j;
+            if (kt < p.m) {
+                // codes 1-4: the reference leaves the caller's state untouched -> NaN
+                const bool written = (cd == 0) || (cd == 6);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
-                    *reinterpret_cast<double2 *>(row + c * p.plane_stride) =
-                        make_double2(res[0][c], res[1][c]);
+                    row[c * p.plane_stride + kt] = written ? r[c] : nan;
                 }
-                *reinterpret_cast<int2 *>(erow) = make_int2(code[0], code[1]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < kTpl; ++j) {
-                    if (k0 + j < p.m) {
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) row[c * p.plane_stride + j] = res[j][c];
-                        erow[j] = code[j];
-                    }
-                }
+                erow[kt] = cd;
             }
         }
     }
 }
 
-// Classes are independent, so their launches go to forked streams: the small classes fill
-// the tail of the large one instead of running after it.
 template <int CLS>
 void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &launches) {
     const int tiles = l.tile_count[CLS];
@@ -357,9 +328,6 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.row_stride = l.row_stride;
     p.err = l.err;
     p.err_row_stride = l.err_row_stride;
-    p.vec_ok = ((reinterpret_cast<uintptr_t>(l.out) % 16) == 0) && (l.plane_stride % 2 == 0) &&
-               (l.row_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(l.err) % 8) == 0) &&
-               (l.err_row_stride % 2 == 0);
     p.g.radiusearthkm = l.radiusearthkm;
     p.g.xke = l.xke;
     p.g.j2 = l.j2;

@@ -238,6 +238,25 @@ def test_resonant_node_table_long_negative_and_unsorted_spans():
     assert np.array_equal(efull[:, 100:140], epart)
 
 
+def test_long_horizons_years_from_epoch():
+    """Years before/after epoch: secular angles reach 1e5-1e6 rad (range reduction), drag
+    terms decay most LEO members (codes 1 and 6 in bulk), resonant members need thousands of
+    integrator steps (node table exceeded -> in-line fall-back)."""
+    n = 2000
+    b1, b2 = pb.synth_catalog(3, n, seed=31)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, "i", flavor=1)
+    mins = np.array([-5.2e6, -1.0e6, -2.0e5, -43200.0, 43200.0, 2.0e5, 1.0e6, 5.2e6])
+    pv, err = b.propagate_from_epoch(mins)
+    pos, vel = posvel_to_rv(pv)
+    eo, ro, vo, _ = orc.propagate_grid(mins, nthreads=8)
+    sr, sv = oracle_sensitivity_mins(orc, mins)
+    stats = compare_states(err, pos, vel, eo, ro, vo, sr, sv, "long horizons")
+    print(stats)
+    assert stats["codes"][1] > 100 and stats["codes"][6] > 10 and stats["codes"][0] > 2000
+
+
 # ---- N1: TLE text parsed on the device ------------------------------------------------------
 @pytest.mark.parametrize("flavor", [0, 1])
 def test_device_tle_parser_equals_host_parser(flavor):
