@@ -111,6 +111,33 @@ class ClockSampler(threading.Thread):
         }
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the first-touch placement of the pinned host buffers it
+    allocates next) to the NUMA node the GPU hangs off: D2H then stays on the local root
+    complex / memory controller. Returns a short description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return "numa: node %d has no allowed cpus" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa node %d, %d cpus" % (node, len(allowed))
+    except Exception as exc:  # pragma: no cover - depends on the box
+        return "numa: unbound (%s)" % type(exc).__name__
+
+
 def catalogue_lines(workload, rank, world):
     """Global catalogue of world x n satellites, this rank's satellite range."""
     import perturb_b200 as pb
@@ -286,6 +313,8 @@ def run_gpu(args):
         return
 
     # ---- end to end through the C ABI with HOST buffers ----
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     h_jd = torch.tensor(jd).pin_memory()
     h_fr = torch.tensor(fr).pin_memory()
     h_out = torch.empty((6, n, m), dtype=torch.float64).pin_memory()
@@ -301,6 +330,7 @@ def run_gpu(args):
         _ = int(h_err[0, 0])
     e2e_s = time.perf_counter() - te
     e2e_value = evals_step_rank * world * e2e_steps / pb.max_over_ranks(e2e_s, dist, dev)
+    os.sched_setaffinity(0, all_cpus)  # the CPU arm below uses every host core again
     codes_ok = float((h_err == 0).double().mean())
 
     if rank != 0:
@@ -378,6 +408,7 @@ def run_gpu(args):
             "d2h_bytes_per_step": int(evals_step_rank * 52),
             "steps": e2e_steps,
             "host_buffers": "pinned",
+            "placement": numa,
         },
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
