@@ -450,3 +450,38 @@ def test_full_size_c2_30k_by_1440():
     torch.cuda.synchronize()
     assert torch.equal(err2, err[:, 700:764])
     assert torch.equal(out2.nan_to_num(nan=-7.0), out[:, :, 700:764].nan_to_num(nan=-7.0))
+
+
+def test_mega_constellation_shard_beyond_2g_elements():
+    """BASELINE config 5 shape on one GPU: 500 000 satellites x 1200 times = 6e8 evaluations,
+    3.6e9 output doubles (29 GB): element offsets exceed 2^31, plane offsets exceed 2^32."""
+    import torch
+    n, m = 500000, 1200
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs 40 GB of free device memory")
+    b1, b2 = pb.synth_catalog(5, n)
+    b = pb.SatelliteBatch.from_text(b1, b2, n=n)
+    assert (b.last_error() == 0).all() and (b.orbit_class() == 0).all()
+    jd, fr = pb.synth_time_grid(m)
+    out = torch.empty((6, n, m), dtype=torch.float64, device="cuda")
+    err = torch.full((n, m), -1, dtype=torch.int32, device="cuda")
+    b.propagate(torch.tensor(jd, device="cuda"), torch.tensor(fr, device="cuda"), out, err)
+    torch.cuda.synchronize()
+    assert bool((err == 0).all())
+    rng = np.random.default_rng(5)
+    pick = np.sort(np.concatenate([rng.choice(n, 61, replace=False), [0, n // 2, n - 1]]))
+    lines1, lines2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    orc = port.OracleSatellites.from_tle_lines([lines1[i] for i in pick], [lines2[i] for i in pick],
+                                               1, "i", flavor=1)
+    eo, ro, vo, _ = orc.propagate_grid(jd, fr, use_jd=True, nthreads=8)
+    sr, sv = oracle_sensitivity_jd(orc, jd, fr)
+    idx = torch.tensor(pick, device="cuda")
+    pos, vel = posvel_to_rv(out[:, idx].cpu().numpy())
+    stats = compare_states(err[idx].cpu().numpy(), pos, vel, eo, ro, vo, sr, sv, "C5 shard sample")
+    print(stats)
+    assert stats["regular"] == len(pick) * m
+    r = torch.linalg.vector_norm(out[0:3], dim=0)
+    assert float(r.min()) > 6700.0 and float(r.max()) < 7100.0  # 14.98-15.14 rev/day shells
+    del out, err, r
+    torch.cuda.empty_cache()
