@@ -200,7 +200,14 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     if (!simp) {
         const double delomg = k(PF_OMGCOF) * t;
-        const double delmtemp = 1.0 + k(PF_ETA) * cos_cw(wrap_pi2(xmdf));
+        // cos(xmdf) and sin(mm) with mm = xmdf + temp, |temp| small (drag corrections): one
+        // sincos of xmdf, then the angle-addition formula with a short series for temp. On
+        // B200 an FP64 instruction blocks its scheduler's issue port for both pipe cycles
+        // (scripts/ubench/fp64_mix.cu), so a select-heavy "one polynomial for sin or cos"
+        // costs more than it saves.
+        double sinm, cosm;
+        sincos_cw(wrap_pi2(xmdf), sinm, cosm);
+        const double delmtemp = 1.0 + k(PF_ETA) * cosm;
         const double delm = k(PF_XMCOF) * (delmtemp * delmtemp * delmtemp - k(PF_DELMO));
         const double temp = delomg + delm;
         mm = xmdf + temp;
@@ -208,7 +215,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double t3 = t2 * t;
         const double t4 = t3 * t;
         tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
-        tempe = tempe + k(PF_BC5) * (sin_cw(wrap_pi2(mm)) - k(PF_SINMAO));
+        double sind, cosd;
+        sincos_small(temp, sind, cosd);
+        const double sin_mm = sinm * cosd + cosm * sind;
+        tempe = tempe + k(PF_BC5) * (sin_mm - k(PF_SINMAO));
         templ = templ + k(PF_T3COF) * t3 + t4 * (k(PF_T4COF) + t * k(PF_T5COF));
     }
 
@@ -432,7 +442,11 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         double tem5 = 1.0 - cs * axnl - sn * aynl;
         tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
-        if (active) {  // lanes that already converged keep their state
+        // Lanes that already converged keep their state. That includes sineo1/coseo1: the
+        // reference keeps sin/cos of the iterate BEFORE the final update (it does not
+        // re-evaluate them), and a result must not depend on whether another lane of the warp
+        // needed one more iteration.
+        if (active) {
             sineo1 = sn;
             coseo1 = cs;
             eo1 = eo1 + tem5;
@@ -494,9 +508,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     double sinsu, cossu, snod, cnod, sini, cosi;
     {
         const double h2 = sinu * sinu + cosu * cosu;
-        const double inv_h = (h2 > 0.0) ? rsqrt_fast(h2) : 0.0;
-        const double su_s = (h2 > 0.0) ? sinu * inv_h : 0.0;  // atan2(0, 0) == 0
-        const double su_c = (h2 > 0.0) ? cosu * inv_h : 1.0;
+        const double inv_h = rsqrt_fast(h2);
+        const bool degenerate = !(h2 > 0.0);  // atan2(0, 0) == 0; selects, not branches
+        const double su_s = degenerate ? 0.0 : sinu * inv_h;
+        const double su_c = degenerate ? 1.0 : cosu * inv_h;
         double sd, cd;
         sincos_small(dsu, sd, cd);
         sinsu = su_s * cd - su_c * sd;

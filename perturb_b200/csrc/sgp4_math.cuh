@@ -104,11 +104,12 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
 }
 
 __device__ __forceinline__ double sqrt_fast(double x) {
-    if (x == 0.0) return 0.0;
     const double y = rsqrt_fast(x);
     const double s = __dmul_rn(x, y);
-    // s <- s + 0.5 y (x - s^2)
-    return __fma_rn(__dmul_rn(y, kMc[MC_HALF]), __fma_rn(-s, s, x), s);
+    // s <- s + 0.5 y (x - s^2); x == 0 gives 0 * inf = NaN, patched by a select (no branch:
+    // branches fence the uniform datapath)
+    const double r = __fma_rn(__dmul_rn(y, kMc[MC_HALF]), __fma_rn(-s, s, x), s);
+    return (x == 0.0) ? 0.0 : r;
 }
 
 // ---- angle reduction -----------------------------------------------------------------------
@@ -224,23 +225,26 @@ __device__ __forceinline__ double cos_cw(double x) { return sin_or_cos_cw<true>(
 // sin and cos of a small angle (|d| < 2^-6) by short Taylor sums; anything larger goes
 // through the general routine. Used for the short-period correction of the argument of
 // latitude, |d| ~ 1e-3 for every physical orbit.
+// The series is evaluated unconditionally (the common case, kept outside any branch so that
+// it stays on the warp-uniform path); a lane whose angle is too large for it -- garbage
+// states only -- overwrites the result through the general routine. The decision is per lane,
+// so a result never depends on which other times share the warp.
 __device__ __forceinline__ void sincos_small(double d, double &s, double &c) {
-    if (fabs(d) < 0.015625) {
-        const double z = __dmul_rn(d, d);
-        // sin d = d (1 - z/6 + z^2/120 - z^3/5040 + z^4/362880), error < 1e-24
-        double p = 2.75573192239858906526e-06;
-        p = __fma_rn(p, z, -1.98412698412698412698e-04);
-        p = __fma_rn(p, z, 8.33333333333333333333e-03);
-        p = __fma_rn(p, z, -1.66666666666666666667e-01);
-        s = __fma_rn(__dmul_rn(d, z), p, d);
-        // cos d = 1 - z/2 + z^2/24 - z^3/720 + z^4/40320 - z^5/3628800
-        double k = -2.75573192239858906526e-07;
-        k = __fma_rn(k, z, 2.48015873015873015873e-05);
-        k = __fma_rn(k, z, -1.38888888888888888889e-03);
-        k = __fma_rn(k, z, 4.16666666666666666667e-02);
-        k = __fma_rn(k, z, -0.5);
-        c = __fma_rn(k, z, 1.0);
-    } else {
+    const double z = __dmul_rn(d, d);
+    // sin d = d (1 - z/6 + z^2/120 - z^3/5040 + z^4/362880), error < 1e-24 for |d| < 2^-6
+    double p = 2.75573192239858906526e-06;
+    p = __fma_rn(p, z, -1.98412698412698412698e-04);
+    p = __fma_rn(p, z, 8.33333333333333333333e-03);
+    p = __fma_rn(p, z, -1.66666666666666666667e-01);
+    s = __fma_rn(__dmul_rn(d, z), p, d);
+    // cos d = 1 - z/2 + z^2/24 - z^3/720 + z^4/40320 - z^5/3628800
+    double k = -2.75573192239858906526e-07;
+    k = __fma_rn(k, z, 2.48015873015873015873e-05);
+    k = __fma_rn(k, z, -1.38888888888888888889e-03);
+    k = __fma_rn(k, z, 4.16666666666666666667e-02);
+    k = __fma_rn(k, z, -0.5);
+    c = __fma_rn(k, z, 1.0);
+    if (!(fabs(d) < 0.015625)) {
         sincos_cw(wrap_pi2(d), s, c);
     }
 }
