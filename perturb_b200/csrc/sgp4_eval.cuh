@@ -426,8 +426,11 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
     // Newton iteration of the reference: at most 10 corrections, stop after one smaller than
-    // 1e-12, clamp a correction to +-0.95; sin/cos kept are those of the LAST EVALUATED
-    // iterate (the reference uses sineo1/coseo1 from before the final update too).
+    // 1e-12, clamp a correction to +-0.95. The reference keeps sin/cos of the iterate BEFORE
+    // the final (sub-1e-12) update and never uses the updated eo1 again, so that last update
+    // is simply not applied here: a converged lane then sits on its evaluation point, any
+    // further warp-level iteration recomputes the very same sn, cs for it, and nothing but
+    // eo1's increment needs masking. Results do not depend on the other lanes of the warp.
     double eo1 = u, sineo1 = 1.0, coseo1 = 1.0;
     bool active = true;
 #pragma unroll 1
@@ -437,21 +440,12 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         } else if (!active) {
             break;
         }
-        double sn, cs;
-        sincos_cw(eo1, sn, cs);
-        double tem5 = 1.0 - cs * axnl - sn * aynl;
-        tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
+        sincos_cw(eo1, sineo1, coseo1);
+        double tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
+        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
-        // Lanes that already converged keep their state. That includes sineo1/coseo1: the
-        // reference keeps sin/cos of the iterate BEFORE the final update (it does not
-        // re-evaluate them), and a result must not depend on whether another lane of the warp
-        // needed one more iteration.
-        if (active) {
-            sineo1 = sn;
-            coseo1 = cs;
-            eo1 = eo1 + tem5;
-            active = fabs(tem5) >= 1.0e-12;
-        }
+        active = active && (fabs(tem5) >= 1.0e-12);
+        eo1 = eo1 + (active ? tem5 : 0.0);
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
