@@ -136,6 +136,18 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
                                      double *posvel, int32_t *err, size_t row_stride,
                                      size_t plane_stride, void *stream);
 
+/* Same evaluation, additionally handing back what `sgp4()` leaves in `Satellite::sat_rec` on
+ * every call (src/sgp4.cpp:1895-1901): the singly averaged mean elements
+ *     elements[e * plane_stride + i * row_stride + k],  e = am, em, im, Om, om, mm, nm
+ * (Earth radii, -, rad, rad, rad, rad, rad/min). They are written when the reference writes
+ * them (codes 0, 3, 4, 6) and are quiet NaN otherwise (codes 1 and 2 return before the store).
+ * jd_frac == NULL selects the `propagate_from_epoch` form with `jd` holding minutes.
+ * All output buffers of this entry point must be DEVICE memory. */
+int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
+                                   const double *jd_frac, size_t m, double *posvel,
+                                   int32_t *err, double *elements, size_t row_stride,
+                                   size_t plane_stride, void *stream);
+
 int perturb_gpu_synchronize(perturb_gpu_batch *batch);
 
 /* ---- queries ------------------------------------------------------------------------- */

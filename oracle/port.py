@@ -69,6 +69,8 @@ def lib():
         L.orc_propagate_grid_diag.restype = C.c_double
         L.orc_propagate_grid_diag.argtypes = L.orc_propagate_grid.argtypes + [
             C.POINTER(C.c_ubyte), dp]
+        L.orc_propagate_grid_elems.restype = C.c_double
+        L.orc_propagate_grid_elems.argtypes = L.orc_propagate_grid.argtypes + [dp]
         L.orc_gstime.restype = C.c_double
         L.orc_gstime.argtypes = [C.c_double]
         _lib = L
@@ -179,3 +181,16 @@ class OracleSatellites:
             err.ctypes.data_as(C.POINTER(C.c_int)),
             self.converged.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(self.cond))
         return err, pos, vel, secs
+
+    def propagate_grid_elements(self, ta, tb=None, use_jd=False, nthreads=1):
+        """(err [n,m], elems [n,m,7] = am, em, im, Om, om, mm, nm as sgp4() leaves them in the
+        record; NaN where the call returned before storing them)."""
+        ta = np.ascontiguousarray(ta, dtype=np.float64)
+        tb = np.ascontiguousarray(tb if tb is not None else np.zeros_like(ta), dtype=np.float64)
+        m = ta.size
+        err = np.zeros((self.n, m), dtype=np.int32)
+        elems = np.zeros((self.n, m, 7))
+        lib().orc_propagate_grid_elems(
+            self.sats, self.n, _dp(ta), _dp(tb), m, int(bool(use_jd)), int(nthreads), None, None,
+            err.ctypes.data_as(C.POINTER(C.c_int)), _dp(elems))
+        return err, elems

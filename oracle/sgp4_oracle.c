@@ -1032,6 +1032,7 @@ typedef struct {
     int *err;
     unsigned char *converged;
     double *cond;
+    double *elems;
 } grid_job;
 
 static void *grid_worker(void *arg) {
@@ -1042,6 +1043,7 @@ static void *grid_worker(void *arg) {
             s.kepler_iters = 0;
             s.kepler_last = 0.0;
             s.cond = 0.0;
+            if (j->elems) s.am = s.em = s.im = s.Om = s.om = s.mm = s.nm = NAN;
             double r[3] = {NAN, NAN, NAN}, v[3] = {NAN, NAN, NAN};
             int e;
             if (j->use_jd)
@@ -1059,6 +1061,11 @@ static void *grid_worker(void *arg) {
             if (j->converged)
                 j->converged[o] = !(s.kepler_iters >= 10 && fabs(s.kepler_last) >= 1.0e-12);
             if (j->cond) j->cond[o] = s.cond;
+            if (j->elems) {
+                double *q = j->elems + o * 7;
+                q[0] = s.am; q[1] = s.em; q[2] = s.im; q[3] = s.Om; q[4] = s.om; q[5] = s.mm;
+                q[6] = s.nm;
+            }
         }
     }
     return NULL;
@@ -1070,9 +1077,25 @@ double orc_propagate_grid(const orc_sat *sats, long n, const double *ta, const d
                                    NULL);
 }
 
+static double grid_run(const orc_sat *sats, long n, const double *ta, const double *tb, long m,
+                       int use_jd, int nthreads, double *pos, double *vel, int *err,
+                       unsigned char *converged, double *cond, double *elems);
+
 double orc_propagate_grid_diag(const orc_sat *sats, long n, const double *ta, const double *tb,
                                long m, int use_jd, int nthreads, double *pos, double *vel,
                                int *err, unsigned char *converged, double *cond) {
+    return grid_run(sats, n, ta, tb, m, use_jd, nthreads, pos, vel, err, converged, cond, NULL);
+}
+
+double orc_propagate_grid_elems(const orc_sat *sats, long n, const double *ta, const double *tb,
+                                long m, int use_jd, int nthreads, double *pos, double *vel,
+                                int *err, double *elems) {
+    return grid_run(sats, n, ta, tb, m, use_jd, nthreads, pos, vel, err, NULL, NULL, elems);
+}
+
+static double grid_run(const orc_sat *sats, long n, const double *ta, const double *tb, long m,
+                       int use_jd, int nthreads, double *pos, double *vel, int *err,
+                       unsigned char *converged, double *cond, double *elems) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 1024) nthreads = 1024;
     struct timespec t0, t1;
@@ -1081,7 +1104,7 @@ double orc_propagate_grid_diag(const orc_sat *sats, long n, const double *ta, co
     grid_job jobs[1024];
     for (int t = 0; t < nthreads; ++t) {
         grid_job j = {sats, n * t / nthreads, n * (t + 1) / nthreads, m, ta, tb, use_jd, pos, vel, err,
-                      converged, cond};
+                      converged, cond, elems};
         jobs[t] = j;
         if (nthreads == 1)
             grid_worker(&jobs[t]);

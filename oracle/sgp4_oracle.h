@@ -98,6 +98,11 @@ double orc_propagate_grid(const orc_sat *sats, long n, const double *ta, const d
 double orc_propagate_grid_diag(const orc_sat *sats, long n, const double *ta, const double *tb,
                                long m, int use_jd, int nthreads, double *pos, double *vel,
                                int *err, unsigned char *converged, double *cond);
+/* Same, also returning what sgp4() leaves in the record per call: elems [n][m][7] = am, em,
+ * im, Om, om, mm, nm; NaN where the call returned before storing them. May be NULL. */
+double orc_propagate_grid_elems(const orc_sat *sats, long n, const double *ta, const double *tb,
+                                long m, int use_jd, int nthreads, double *pos, double *vel,
+                                int *err, double *elems);
 
 int orc_sizeof_sat(void);
 

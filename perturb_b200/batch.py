@@ -240,6 +240,26 @@ class SatelliteBatch:
             self.synchronize()
         return posvel, err
 
+    def propagate_elements(self, jd, jd_frac=None, stream=None):
+        """propagate (or propagate_from_epoch when jd_frac is None, jd = minutes) that also
+        returns the mean elements sgp4() leaves in sat_rec: (posvel [6,n,m], err [n,m],
+        elements [7,n,m] = am, em, im, Om, om, mm, nm), all as torch CUDA tensors."""
+        import torch
+        dev = torch.device("cuda", capi.lib().perturb_gpu_device(self._h))
+        m = int(jd.shape[0])
+        d_a = torch.as_tensor(jd, dtype=torch.float64, device=dev)
+        d_b = None if jd_frac is None else torch.as_tensor(jd_frac, dtype=torch.float64, device=dev)
+        m2 = m + (m & 1)
+        posvel = torch.empty((6, self.n, m2), dtype=torch.float64, device=dev)[:, :, :m]
+        elements = torch.empty((7, self.n, m2), dtype=torch.float64, device=dev)[:, :, :m]
+        err = torch.empty((self.n, m2), dtype=torch.int32, device=dev)[:, :m]
+        st = capi.lib().perturb_gpu_propagate_elements(
+            self._h, _ptr(d_a), _ptr(d_b), m, _ptr(posvel), _ptr(err), _ptr(elements), m2,
+            self.n * m2, stream)
+        capi.check(st, "perturb_gpu_propagate_elements")
+        self.synchronize()
+        return posvel, err, elements
+
     def propagate_from_epoch(self, mins, posvel=None, err=None, stream=None, sync=True):
         m = int(mins.shape[0])
         posvel, err = self._outputs(m, posvel, err)

@@ -446,7 +446,7 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
 
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
                    size_t m, double *posvel, int32_t *err, size_t row_stride,
-                   size_t plane_stride, void *stream_arg) {
+                   size_t plane_stride, void *stream_arg, double *elements = nullptr) {
     if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
     b->last_launches = 0;
     if (m == 0 || b->n == 0) return PERTURB_GPU_OK;
@@ -485,6 +485,11 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     pb::PropLaunch l;
     fill_launch(b, l);
     l.use_jd = use_jd ? 1 : 0;
+    l.elements = elements;
+    if (elements != nullptr && !(is_device_pointer(elements) && is_device_pointer(posvel) &&
+                                 is_device_pointer(err))) {
+        return fail(PERTURB_GPU_ERR_ARG, "propagate_elements needs device output buffers");
+    }
 
     const bool out_dev = is_device_pointer(posvel);
     const bool err_dev = is_device_pointer(err);
@@ -622,6 +627,15 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
                                      size_t plane_stride, void *stream) {
     return propagate_impl(batch, mins, nullptr, false, m, posvel, err, row_stride, plane_stride,
                           stream);
+}
+
+int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
+                                   const double *jd_frac, size_t m, double *posvel,
+                                   int32_t *err, double *elements, size_t row_stride,
+                                   size_t plane_stride, void *stream) {
+    if (elements == nullptr) return fail(PERTURB_GPU_ERR_ARG, "elements is null");
+    return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m, posvel, err, row_stride,
+                          plane_stride, stream, elements);
 }
 
 int perturb_gpu_synchronize(perturb_gpu_batch *batch) {

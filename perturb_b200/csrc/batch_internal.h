@@ -51,6 +51,7 @@ struct PropLaunch {
     size_t plane_stride, row_stride;
     int32_t *err;  // err[sat * err_row_stride + k]
     size_t err_row_stride;
+    double *elements;  // optional 7 planes am, em, im, Om, om, mm, nm (same strides as out)
     double radiusearthkm, xke, j2, j3oj2;
     int opsmode_a;
     // resonance node table scratch (null / 0: resonant evaluations integrate in-line)

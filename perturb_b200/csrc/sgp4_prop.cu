@@ -75,6 +75,7 @@ struct PropParams {
     size_t plane_stride, row_stride;
     int32_t *err;
     size_t err_row_stride;
+    double *elements;
     GravConsts g;
     int opsmode_a;
     // resonance node table (deep-space resonant classes only)
@@ -196,7 +197,7 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     }
 }
 
-template <int CLS>
+template <int CLS, bool WANT_ELEMENTS>
 __global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR : PB_MIN_BLOCKS_DEEP)
 sgp4_prop_kernel(const PropParams p) {
     using TF = TileFields<CLS>;
@@ -272,9 +273,23 @@ sgp4_prop_kernel(const PropParams p) {
             const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[1], (j == 0) ? tb[0] : tb[1],
                                        k(PF_JD0), k(PF_JDF0));
             double r[6];
-            const int cd = sgp4_eval<CLS, false, true>(k, p.g, p.opsmode_a != 0, no_flags, t, r,
-                                                       nullptr, kResonant ? &nodes : nullptr);
+            Sgp4Side side;
+            const int cd = sgp4_eval<CLS, WANT_ELEMENTS, true>(
+                k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
+                kResonant ? &nodes : nullptr);
             const int kt = k_base + i0 + 32 * j;
+            if (WANT_ELEMENTS && kt < p.m) {
+                // what sgp4() leaves in satrec (src/sgp4.cpp:1895-1901); not reached for codes 1, 2
+                const bool stored = side.stage >= 1;
+                double *erow_el = p.elements + static_cast<size_t>(dst) * p.row_stride + kt;
+                erow_el[0 * p.plane_stride] = stored ? side.am : nan;
+                erow_el[1 * p.plane_stride] = stored ? side.em : nan;
+                erow_el[2 * p.plane_stride] = stored ? side.im : nan;
+                erow_el[3 * p.plane_stride] = stored ? side.Om : nan;
+                erow_el[4 * p.plane_stride] = stored ? side.om : nan;
+                erow_el[5 * p.plane_stride] = stored ? side.mm : nan;
+                erow_el[6 * p.plane_stride] = stored ? side.nm : nan;
+            }
             if (kt < p.m) {
                 // codes 1-4: the reference leaves the caller's state untouched -> NaN
                 const bool written = (cd == 0) || (cd == 6);
@@ -301,7 +316,11 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
         stream = l.aux[CLS];
         cudaStreamWaitEvent(stream, l.fork, 0);
     }
-    sgp4_prop_kernel<CLS><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    if (p.elements != nullptr) {
+        sgp4_prop_kernel<CLS, true><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    } else {
+        sgp4_prop_kernel<CLS, false><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    }
     if (forked) {
         cudaEventRecord(l.join[CLS], stream);
         cudaStreamWaitEvent(main, l.join[CLS], 0);
@@ -328,6 +347,7 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.row_stride = l.row_stride;
     p.err = l.err;
     p.err_row_stride = l.err_row_stride;
+    p.elements = l.elements;
     p.g.radiusearthkm = l.radiusearthkm;
     p.g.xke = l.xke;
     p.g.j2 = l.j2;

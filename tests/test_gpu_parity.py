@@ -257,6 +257,51 @@ def test_long_horizons_years_from_epoch():
     assert stats["codes"][1] > 100 and stats["codes"][6] > 10 and stats["codes"][0] > 2000
 
 
+# ---- N2: mean elements sgp4() leaves in sat_rec --------------------------------------------------
+@pytest.mark.parametrize("use_jd", [True, False])
+def test_mean_element_side_outputs(use_jd):
+    """perturb_gpu_propagate_elements: am, em, im, Om, om, mm, nm per evaluation, stored exactly
+    when the reference stores them (src/sgp4.cpp:1895-1901)."""
+    l1, l2 = ver_lines(G)
+    n = 2500
+    b1, b2 = pb.synth_catalog(3, n, seed=13)
+    L1 = l1 + pb.block_to_lines(b1, n)
+    L2 = l2 + pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, "i", flavor=1)
+    if use_jd:
+        jd, fr = pb.synth_time_grid(10080)
+        sel = np.linspace(0, 10079, 61).astype(int)
+        ta, tb = jd[sel], fr[sel]
+        sr, sv = oracle_sensitivity_jd(orc, ta, tb)
+    else:
+        ta, tb = np.linspace(-1440.0, 20000.0, 57), None
+        sr, sv = oracle_sensitivity_mins(orc, ta)
+    pv, err, el = b.propagate_elements(ta, tb)
+    eo, elo = orc.propagate_grid_elements(ta, tb, use_jd=use_jd, nthreads=8)
+    err, el = err.cpu().numpy(), np.moveaxis(el.cpu().numpy(), 0, -1)
+    assert np.array_equal(err, eo)
+    stored = np.isfinite(elo[..., 0])
+    assert np.array_equal(stored, np.isin(eo, (0, 3, 4, 6)))  # codes 1, 2 return before the store
+    assert np.isnan(el[~stored]).all() and np.isfinite(el[stored]).all()
+    # the plain entry point gives the same states and codes
+    pv2, err2 = b.propagate(ta, tb) if use_jd else b.propagate_from_epoch(ta)
+    assert np.array_equal(err2, err)
+    regular = stored & (64.0 * sr <= 1e-6) & (64.0 * sv <= 1e-9) & np.isin(eo, (0, 6))
+    assert regular.sum() > 0.9 * stored.sum()
+    dstate = np.abs(pv.cpu().numpy() - pv2)[:, regular]
+    assert dstate[0:3].max() < 1e-7 and dstate[3:6].max() < 1e-10  # fmod vs wrap rounding only
+    g, o = el[regular], elo[regular]
+    for j, name in enumerate(("am", "em", "im")):
+        assert np.abs(g[:, j] - o[:, j]).max() < 1e-11 * max(1.0, np.abs(o[:, j]).max()), name
+    for j, name in ((3, "Om"), (4, "om"), (5, "mm")):
+        d = np.abs((g[:, j] - o[:, j] + np.pi) % (2 * np.pi) - np.pi)
+        assert d.max() < 1e-9, (name, d.max())
+        same_branch = np.abs(g[:, j] - o[:, j]) < 1e-9
+        assert same_branch.mean() > 0.999, name  # C fmod representative, not just mod 2 pi
+    assert np.abs(g[:, 6] / o[:, 6] - 1.0).max() < 1e-11
+
+
 # ---- N1: TLE text parsed on the device ------------------------------------------------------
 @pytest.mark.parametrize("flavor", [0, 1])
 def test_device_tle_parser_equals_host_parser(flavor):
