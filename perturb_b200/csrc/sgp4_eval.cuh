@@ -57,19 +57,67 @@ struct ClassTraits<PB_CLS_RUNTIME> {
     static constexpr int kIrez = 0;
 };
 
-// Resonance terms at one integrator node, src/sgp4.cpp:1097-1126. Written with explicit
-// fused operations: the node table (built by a pre-pass kernel) and the in-line fall-back
-// must produce the same bits no matter how the compiler would contract either copy.
+// Resonance terms at one integrator node, src/sgp4.cpp:1097-1126.
+//
+// The reference evaluates 3 (24 h) or 10 (12 h) sines and as many cosines of sums of xli, xomi
+// and fixed phases. Here sin/cos of xli (and xomi) are taken ONCE and every term follows
+// from angle-addition / double- / triple-angle identities with the phases' sines and cosines
+// as compile-time constants: 2 sincos + ~70 FMA-class operations instead of 10 sincos with
+// their range reductions (12 h case). Value-preserving up to rounding (a few 1e-16).
+// Written with explicit fused operations: the node table (built by a pre-pass kernel) and the
+// in-line fall-back must produce the same bits no matter how the compiler would contract
+// either copy.
+namespace res {
+// sin / cos of the phase constants of src/sgp4.cpp:1036-1043 (the doubles the reference uses)
+constexpr double s_fasx2 = 0.13093206501640100313, c_fasx2 = 0.99139134268488593686;  // 0.13130908
+constexpr double s_fasx4 = 0.25444411220371228015, c_fasx4 = -0.96708747989251968989; // 2.8843198
+constexpr double s_fasx6 = 0.36578942533149936234, c_fasx6 = 0.93069763957778009002;  // 0.37448087
+constexpr double s_g22 = -0.49213943048915524715, c_g22 = 0.87051638752972935101;     // 5.7686396
+constexpr double s_g32 = 0.81481440616389247062, c_g32 = 0.57972190187001152474;      // 0.95240898
+constexpr double s_g44 = 0.97350577801807993413, c_g44 = -0.22866241528815546759;     // 1.8014998
+constexpr double s_g52 = 0.86783740128127729936, c_g52 = 0.49684831179884195924;      // 1.0508330
+constexpr double s_g54 = -0.95489237761530004228, c_g54 = -0.29695209575316896683;    // 4.4108898
+
+// (sin, cos) of a + b from those of a and b
+__device__ __forceinline__ void add(double sa, double ca, double sb, double cb, double &s,
+                                    double &c) {
+    s = __fma_rn(sa, cb, __dmul_rn(ca, sb));
+    c = __fma_rn(ca, cb, -__dmul_rn(sa, sb));
+}
+// (sin, cos) of a - b
+__device__ __forceinline__ void sub(double sa, double ca, double sb, double cb, double &s,
+                                    double &c) {
+    s = __fma_rn(sa, cb, -__dmul_rn(ca, sb));
+    c = __fma_rn(ca, cb, __dmul_rn(sa, sb));
+}
+// accumulate weight * (sin, cos)(a - phase) into (xs, xc), for two terms sharing the phase:
+// w1 (S1, C1) + w2 (S2, C2), then one rotation by the phase
+__device__ __forceinline__ void pair(double w1, double s1, double c1, double w2, double s2,
+                                     double c2, double sg, double cg, double &xs, double &xc) {
+    const double ss = __fma_rn(w2, s2, __dmul_rn(w1, s1));
+    const double cc = __fma_rn(w2, c2, __dmul_rn(w1, c1));
+    xs = __dadd_rn(xs, __fma_rn(ss, cg, -__dmul_rn(cc, sg)));
+    xc = __dadd_rn(xc, __fma_rn(cc, cg, __dmul_rn(ss, sg)));
+}
+}  // namespace res
+
 template <class K>
 __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli, double xni,
                                                 double atime, double &xndt, double &xldot,
                                                 double &xnddt) {
+    double sl, cl;
+    sincos_cw(wrap_pi2(xli), sl, cl);
     if (irez != 2) {
-        constexpr double fasx2 = 0.13130908, fasx4 = 2.8843198, fasx6 = 0.37448087;
-        double s1, c1, s2, c2, s3, c3;
-        sincos_cw(wrap_pi2(__dsub_rn(xli, fasx2)), s1, c1);
-        sincos_cw(wrap_pi2(__dmul_rn(2.0, __dsub_rn(xli, fasx4))), s2, c2);
-        sincos_cw(wrap_pi2(__dmul_rn(3.0, __dsub_rn(xli, fasx6))), s3, c3);
+        // theta1 = xli - fasx2, theta2 = 2 (xli - fasx4), theta3 = 3 (xli - fasx6)
+        double s1, c1, s, c;
+        res::sub(sl, cl, res::s_fasx2, res::c_fasx2, s1, c1);
+        res::sub(sl, cl, res::s_fasx4, res::c_fasx4, s, c);
+        const double s2 = __dmul_rn(__dadd_rn(s, s), c);
+        const double c2 = __fma_rn(-__dadd_rn(s, s), s, 1.0);
+        res::sub(sl, cl, res::s_fasx6, res::c_fasx6, s, c);
+        const double f = __fma_rn(-4.0 * s, s, 1.0);        // 1 - 4 s^2
+        const double s3 = __dmul_rn(s, __dadd_rn(f, 2.0));  // s (3 - 4 s^2)
+        const double c3 = __dmul_rn(c, f);                   // c (4 c^2 - 3) = c (1 - 4 s^2)
         const double del1 = k(PF_DEL1), del2 = k(PF_DEL2), del3 = k(PF_DEL3);
         xndt = __fma_rn(del3, s3, __fma_rn(del2, s2, __dmul_rn(del1, s1)));
         xldot = __dadd_rn(xni, k(PF_XFACT));
@@ -77,48 +125,32 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
                          __fma_rn(__dmul_rn(2.0, del2), c2, __dmul_rn(del1, c1)));
         xnddt = __dmul_rn(xnddt, xldot);
     } else {
-        constexpr double g22 = 5.7686396, g32 = 0.95240898, g44 = 1.8014998, g52 = 1.0508330,
-                         g54 = 4.4108898;
         const double xomi = __fma_rn(k(PF_ARGPDOT), atime, k(PF_ARGPO));
-        const double x2omi = __dadd_rn(xomi, xomi);
-        const double x2li = __dadd_rn(xli, xli);
-        const double a22 = __dsub_rn(xli, g22), a32 = __dsub_rn(xli, g32);
-        const double a52 = __dsub_rn(xli, g52), a44 = __dsub_rn(x2li, g44);
-        const double a54 = __dsub_rn(x2li, g54);
-        double s, c, sa, ca, cb;
-        sincos_cw(wrap_pi2(__dadd_rn(x2omi, a22)), s, c);
-        sa = __dmul_rn(k(PF_D2201), s);
-        ca = __dmul_rn(k(PF_D2201), c);
-        sincos_cw(wrap_pi2(a22), s, c);
-        sa = __fma_rn(k(PF_D2211), s, sa);
-        ca = __fma_rn(k(PF_D2211), c, ca);
-        sincos_cw(wrap_pi2(__dadd_rn(xomi, a32)), s, c);
-        sa = __fma_rn(k(PF_D3210), s, sa);
-        ca = __fma_rn(k(PF_D3210), c, ca);
-        sincos_cw(wrap_pi2(__dsub_rn(a32, xomi)), s, c);
-        sa = __fma_rn(k(PF_D3222), s, sa);
-        ca = __fma_rn(k(PF_D3222), c, ca);
-        sincos_cw(wrap_pi2(__dadd_rn(x2omi, a44)), s, c);
-        sa = __fma_rn(k(PF_D4410), s, sa);
-        cb = __dmul_rn(k(PF_D4410), c);
-        sincos_cw(wrap_pi2(a44), s, c);
-        sa = __fma_rn(k(PF_D4422), s, sa);
-        cb = __fma_rn(k(PF_D4422), c, cb);
-        sincos_cw(wrap_pi2(__dadd_rn(xomi, a52)), s, c);
-        sa = __fma_rn(k(PF_D5220), s, sa);
-        ca = __fma_rn(k(PF_D5220), c, ca);
-        sincos_cw(wrap_pi2(__dsub_rn(a52, xomi)), s, c);
-        sa = __fma_rn(k(PF_D5232), s, sa);
-        ca = __fma_rn(k(PF_D5232), c, ca);
-        sincos_cw(wrap_pi2(__dadd_rn(xomi, a54)), s, c);
-        sa = __fma_rn(k(PF_D5421), s, sa);
-        cb = __fma_rn(k(PF_D5421), c, cb);
-        sincos_cw(wrap_pi2(__dsub_rn(a54, xomi)), s, c);
-        sa = __fma_rn(k(PF_D5433), s, sa);
-        cb = __fma_rn(k(PF_D5433), c, cb);
-        xndt = sa;
+        double so, co;
+        sincos_cw(wrap_pi2(xomi), so, co);
+        const double s2o = __dmul_rn(__dadd_rn(so, so), co), c2o = __fma_rn(-__dadd_rn(so, so), so, 1.0);
+        const double s2l = __dmul_rn(__dadd_rn(sl, sl), cl), c2l = __fma_rn(-__dadd_rn(sl, sl), sl, 1.0);
+        double sA, cA, sB, cB;
+        double xs = 0.0, xc = 0.0;   // sum of d sin(..), sum of d cos(..) for the l = 2 terms
+        double ys = 0.0, yc = 0.0;   // same for the terms the reference doubles in xnddt (44, 54)
+        // g22: (2 xomi + xli), (xli)
+        res::add(s2o, c2o, sl, cl, sA, cA);
+        res::pair(k(PF_D2201), sA, cA, k(PF_D2211), sl, cl, res::s_g22, res::c_g22, xs, xc);
+        // g32 and g52 share (xomi + xli), (xli - xomi)
+        res::add(so, co, sl, cl, sA, cA);
+        res::sub(sl, cl, so, co, sB, cB);
+        res::pair(k(PF_D3210), sA, cA, k(PF_D3222), sB, cB, res::s_g32, res::c_g32, xs, xc);
+        res::pair(k(PF_D5220), sA, cA, k(PF_D5232), sB, cB, res::s_g52, res::c_g52, xs, xc);
+        // g44: (2 xomi + 2 xli), (2 xli)
+        res::add(s2o, c2o, s2l, c2l, sA, cA);
+        res::pair(k(PF_D4410), sA, cA, k(PF_D4422), s2l, c2l, res::s_g44, res::c_g44, ys, yc);
+        // g54: (xomi + 2 xli), (2 xli - xomi)
+        res::add(so, co, s2l, c2l, sA, cA);
+        res::sub(s2l, c2l, so, co, sB, cB);
+        res::pair(k(PF_D5421), sA, cA, k(PF_D5433), sB, cB, res::s_g54, res::c_g54, ys, yc);
+        xndt = __dadd_rn(xs, ys);
         xldot = __dadd_rn(xni, k(PF_XFACT));
-        xnddt = __dmul_rn(__fma_rn(2.0, cb, ca), xldot);
+        xnddt = __dmul_rn(__fma_rn(2.0, yc, xc), xldot);
     }
 }
 
@@ -324,9 +356,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     double sinip, cosip, aycof, xlcof;
     if (deep) {
         constexpr double zns = 1.19459e-5, zes = 0.01675, znl = 1.5835218e-4, zel = 0.05490;
-        double zm, zf, sinzf, coszf, f2, f3, s0, c0;
+        double zm, zf, sinzf, coszf, f2, f3, s0, c0, sinzm, unused;
         zm = k(PF_ZMOS) + zns * t;
-        zf = zm + 2.0 * zes * sin_cw(wrap_pi2(zm));
+        sincos_cw(wrap_pi2(zm), sinzm, unused);  // cheaper in issue slots than a select-based sin
+        zf = zm + 2.0 * zes * sinzm;
         sincos_cw(wrap_pi2(zf), sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
@@ -336,7 +369,8 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double sghs = k(PF_SGH2) * f2 + k(PF_SGH3) * f3 + k(PF_SGH4) * sinzf;
         const double shs = k(PF_SH2) * f2 + k(PF_SH3) * f3;
         zm = k(PF_ZMOL) + znl * t;
-        zf = zm + 2.0 * zel * sin_cw(wrap_pi2(zm));
+        sincos_cw(wrap_pi2(zm), sinzm, unused);
+        zf = zm + 2.0 * zel * sinzm;
         sincos_cw(wrap_pi2(zf), sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
