@@ -459,13 +459,18 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double xl = mp + argpp + nodep + temp * xlcof * axnl;
 
     const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
-    // Newton iteration of the reference: at most 10 corrections, stop after one smaller than
-    // 1e-12, clamp a correction to +-0.95. The reference keeps sin/cos of the iterate BEFORE
-    // the final (sub-1e-12) update and never uses the updated eo1 again, so that last update
-    // is simply not applied here: a converged lane then sits on its evaluation point, any
-    // further warp-level iteration recomputes the very same sn, cs for it, and nothing but
-    // eo1's increment needs masking. Results do not depend on the other lanes of the warp.
-    double eo1 = u, sineo1 = 1.0, coseo1 = 1.0;
+    // Newton iteration of the reference (at most 10 corrections tem5, each clamped to +-0.95,
+    // stop after one smaller than 1e-12; the sin/cos it keeps are those of the iterate BEFORE
+    // that last correction, which is never applied to them).
+    //
+    // Two observations make this cheaper without leaving the reference's fixed point:
+    //  * Newton converges quadratically, so once a correction d is below 6e-8 the NEXT one
+    //    would be < e d^2 / (2 (1 - e)) < 1e-12: the reference's next pass only re-evaluates
+    //    sin/cos at E + d and stops. That pass is replaced by rotating (sin E, cos E) by d
+    //    (second-order series, error < 1e-22) after the loop.
+    //  * a lane that has finished keeps its state, so a result never depends on how many
+    //    iterations the other lanes of the warp (other times of the same satellite) need.
+    double eo1 = u, sineo1 = 1.0, coseo1 = 1.0, dfin = 0.0;
     bool active = true;
 #pragma unroll 1
     for (int ktr = 1; ktr <= 10; ++ktr) {
@@ -474,12 +479,33 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         } else if (!active) {
             break;
         }
-        sincos_cw(eo1, sineo1, coseo1);
-        double tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
-        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
+        double sn, cs;
+        sincos_cw(eo1, sn, cs);
+        double tem5 = 1.0 - cs * axnl - sn * aynl;
+        tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
         if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
-        active = active && (fabs(tem5) >= 1.0e-12);
-        eo1 = eo1 + (active ? tem5 : 0.0);
+        const double mag = fabs(tem5);
+        if (active) {
+            sineo1 = sn;
+            coseo1 = cs;
+            if (!(mag >= 1.0e-12)) {
+                active = false;  // the reference stops here, state as evaluated
+            } else if (mag < 5.9604644775390625e-8 && ktr < 10) {
+                dfin = tem5;     // the reference would make one confirming pass at E + d
+                active = false;
+            } else {
+                eo1 = eo1 + tem5;
+            }
+        }
+    }
+    {   // sin/cos at E + dfin (identity when dfin == 0)
+        const double h = dfin * dfin;
+        const double sd = __fma_rn(-0.16666666666666666 * h, dfin, dfin);
+        const double cd = __fma_rn(-0.5, h, 1.0);
+        const double s_rot = __fma_rn(coseo1, sd, sineo1 * cd);
+        const double c_rot = __fma_rn(-sineo1, sd, coseo1 * cd);
+        sineo1 = s_rot;
+        coseo1 = c_rot;
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
@@ -527,7 +553,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     // (sinu, cosu)/hypot by the small angle dsu instead: no atan2, no second range reduction.
     const double dsu = 0.25 * temp2 * x7thm1 * sin2u;
     const double xnode = nodep + 1.5 * temp2 * cosip * sin2u;
-    const double xinc = xincp + 1.5 * temp2 * cosip * sinip * cos2u;
+    const double dxi = 1.5 * temp2 * cosip * sinip * cos2u;  // xinc = xincp + dxi
     const double nmt = nm * temp1 * g.inv_xke;
     const double mvt = rdotl - nmt * x1mth2 * sin2u;
     const double rvdot = rvdotl + nmt * (x1mth2 * cos2u + 1.5 * con41);
@@ -546,7 +572,13 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         cossu = su_c * cd + su_s * sd;
     }
     sincos_cw(deep ? wrap_pi2(xnode) : xnode, snod, cnod);
-    sincos_cw(deep ? wrap_pi2(xinc) : xinc, sini, cosi);
+    {
+        // xinc = xincp + dxi with dxi ~ 1e-3 and sin/cos(xincp) already at hand
+        double sdx, cdx;
+        sincos_small(dxi, sdx, cdx);
+        sini = sinip * cdx + cosip * sdx;
+        cosi = cosip * cdx - sinip * sdx;
+    }
     const double xmx = -snod * cosi;
     const double xmy = cnod * cosi;
     const double ux = xmx * sinsu + cnod * cossu;
