@@ -1,21 +1,24 @@
 // Device FP64 math for the SGP4/SDP4 kernels (sm_100a).
 //
 // The reference calls glibc's sin/cos/fmod/pow/atan2 (L0 of the layer map). On B200 the
-// path is FP64-pipe bound and -- measured with ncu on the first version -- issue bound: of
-// ~1475 warp instructions per evaluation only ~560 were FP64, the rest were constant
-// materialisation (UMOV/IMAD.MOV pairs for every double literal), slow-path guards of
-// libdevice div/sqrt/sincos and quadrant logic. Hence:
-//   * every polynomial coefficient lives in __constant__ memory, so DFMA takes it as a
-//     constant-bank operand instead of two moves;
-//   * sincos: 3-constant Cody-Waite reduction + minimax kernels on [-pi/4, pi/4], no slow
-//     path: callers pass angles that are already reduced (or reduce them with wrap_pi2);
-//     single sin / cos select ONE coefficient set by quadrant parity instead of evaluating both;
+// path is bound by the FP64 pipe AND by issue slots: an FP64 instruction holds its
+// scheduler's issue port for both pipe cycles (scripts/ubench/fp64_mix.cu), so every
+// non-FP64 instruction costs time as well. The first version spent ~1475 warp instructions
+// per evaluation of which ~560 were FP64 (ncu): constant materialisation (two UMOV per
+// double literal), libdevice slow-path guards around div/sqrt/sincos, quadrant logic. Hence:
+//   * polynomial and reduction constants live in one __constant__ table, fetched two at a
+//     time into uniform registers (LDCU.128) instead of two moves each;
+//   * sincos: 3-constant Cody-Waite reduction + minimax kernels on [-pi/4, pi/4] evaluated
+//     Estrin-style, no slow path: callers pass angles that are already reduced (or reduce
+//     them with wrap_pi2); small angles use a short series (sincos_small);
 //   * fmod(x, 2pi): one FMA-exact reduction with the C `fmod` sign convention (libdevice's
 //     fmod is a bit-serial integer loop); wrap_pi where only the angle mod 2pi matters;
-//   * division / sqrt: MUFU seed + Newton steps, no denormal/overflow fix-up call;
+//   * division / sqrt: MUFU seed + Newton steps, no denormal/overflow fix-up call, selects
+//     instead of branches (a branch fences the uniform datapath);
 //   * pow(x, 2/3) -> cbrt(x)^2, pow(x, 1.5) -> x*sqrt(x).
 // None of these is bit-identical to glibc; the parity budget (1e-6 km, 1e-9 km/s) leaves
-// about three decimal orders over their rounding error (tests/test_gpu_parity.py).
+// about two decimal orders over their rounding error (tests/test_gpu_parity.py); their own
+// error bounds are tested in tests/test_gpu_math.py.
 #ifndef PERTURB_B200_SGP4_MATH_CUH
 #define PERTURB_B200_SGP4_MATH_CUH
 
@@ -26,8 +29,7 @@ namespace pb {
 constexpr double kPi = 3.14159265358979323846;  // src/sgp4.cpp:69
 constexpr double kTwoPi = 2.0 * kPi;
 
-// Constant-bank table (index names below). Kept in one array so that the compiler addresses
-// it as c[3][imm] operands.
+// Constant-bank table (index names below), one array so that neighbours load pairwise.
 enum {
     MC_RINT_MAGIC = 0,  // 1.5 * 2^52
     MC_INV_TWOPI,
@@ -199,7 +201,9 @@ __device__ __forceinline__ void sincos_cw(double x, double &s, double &c) {
 }
 
 // One of sin/cos only: which kernel is needed depends on quadrant parity, and both kernels
-// have the same Horner shape, so the coefficients are selected and ONE polynomial is run.
+// have the same shape, so the coefficients are selected and ONE polynomial is run. Fewer FP64
+// operations than sincos_cw but ~40 selects / constant loads: on B200 that is slower in the
+// hot path (see the header), so the evaluation kernels use sincos_cw; kept for the probe.
 template <bool WANT_COS>
 __device__ __forceinline__ double sin_or_cos_cw(double x) {
     int q;
