@@ -278,19 +278,41 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             const int kk = (t > 0.0) ? n : -n;
             double atime, xni, xli;
             double xndt, xldot, xnddt;
-            if (nodes != nullptr && kk >= nodes->k0 && kk < nodes->k0 + nodes->count) {
-                const double2 st = nodes->base[static_cast<size_t>(kk - nodes->k0) * nodes->stride];
+            // Start from the tabulated node nearest to step kk on the way from epoch (same
+            // direction, not beyond kk); walk whatever is left in-line. With the whole grid
+            // inside the table this is one 16 B load and no step at all.
+            int kj = 0;  // step index the walk starts from (0 = epoch)
+            bool from_table = false;
+            if (nodes != nullptr && nodes->count > 0) {
+                const int k1 = nodes->k0 + nodes->count - 1;  // last tabulated index
+                if (kk >= 0) {
+                    const int cand = kk < k1 ? kk : k1;
+                    if (cand >= nodes->k0 && cand >= 0) {
+                        kj = cand;
+                        from_table = true;
+                    }
+                } else {
+                    const int cand = kk > nodes->k0 ? kk : nodes->k0;
+                    if (cand <= k1 && cand <= 0) {
+                        kj = cand;
+                        from_table = true;
+                    }
+                }
+            }
+            if (from_table) {
+                const double2 st = nodes->base[static_cast<size_t>(kj - nodes->k0) * nodes->stride];
                 xli = st.x;
                 xni = st.y;
-                atime = __dmul_rn(delt, static_cast<double>(n));
+                atime = __dmul_rn(720.0, static_cast<double>(kj));
             } else {
                 atime = 0.0;
                 xni = no;
                 xli = k(PF_XLAMO);
-                for (int i = 0; i < n; ++i) {
-                    resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
-                    resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
-                }
+            }
+            const int left = (kk >= 0) ? kk - kj : kj - kk;
+            for (int i = 0; i < left; ++i) {
+                resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+                resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
             }
             resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
             const double ft = t - atime;

@@ -165,7 +165,7 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     int k_lo = (t_a > 0.0) ? n_a : -n_a;
     int k_hi = (t_b > 0.0) ? n_b : -n_b;
     if (k_lo > k_hi) { const int tmp = k_lo; k_lo = k_hi; k_hi = tmp; }
-    const int kMaxWalk = 1 << 16;  // ~90 years of 720-minute steps
+    const int kMaxWalk = 1400000;  // resonance_step_count() never exceeds 1e9 / 720
     int count = k_hi - k_lo + 1;
     if (count > cap) count = cap;
     if (k_lo < -kMaxWalk || k_hi > kMaxWalk) count = 0;  // evaluations fall back to in-line steps

@@ -64,8 +64,13 @@ def oracle_sensitivity_jd(orc, jd, fr):
 
 
 def compare_states(err, pos, vel, ref_err, ref_pos, ref_vel, sens_r=None, sens_v=None,
-                   what=""):
-    """Asserts the parity bar. pos/vel [..., 3]; returns a dict of worst-case figures."""
+                   what="", horizon_min=None):
+    """Asserts the parity bar. pos/vel [..., 3]; returns a dict of worst-case figures.
+
+    horizon_min: |tsince| per time (broadcast over the last axis of err). The bar is stated
+    for a 7-day horizon; rounding differences grow at least linearly with time (thousands of
+    integrator steps, mean anomaly ~ n t), so beyond 7 days it is scaled by |t| / 7 d. Only
+    the decades-from-epoch tests pass this."""
     err = np.asarray(err)
     ref_err = np.asarray(ref_err)
     mism = err != ref_err
@@ -79,6 +84,10 @@ def compare_states(err, pos, vel, ref_err, ref_pos, ref_vel, sens_r=None, sens_v
     dv = np.abs(vel - ref_vel).max(-1)
     tol_r = np.full(err.shape, TOL_POS_KM)
     tol_v = np.full(err.shape, TOL_VEL_KMS)
+    if horizon_min is not None:
+        scale = np.maximum(1.0, np.abs(np.asarray(horizon_min, dtype=np.float64)) / 10080.0)
+        tol_r = tol_r * scale
+        tol_v = tol_v * scale
     if sens_r is not None:
         tol_r = tol_r + SENS_GAIN * sens_r
         tol_v = tol_v + SENS_GAIN * sens_v
