@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs the quick (device-resident) bench for every library variant under perturb_b200/variants.
-# usage: scripts/sweep_variants.sh "c2 c3 c4" [steps]
+# usage: scripts/sweep_variants.sh "c2 c3s c4s" [steps]
 WL=${1:-c2}
 STEPS=${2:-10}
 for lib in perturb_b200/variants/*.so; do
