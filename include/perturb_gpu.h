@@ -148,6 +148,20 @@ int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
                                    int32_t *err, double *elements, size_t row_stride,
                                    size_t plane_stride, void *stream);
 
+/* Replaces `ClassicalOrbitalElements(StateVector, GravModel)` (src/perturb.cpp:119-131, i.e.
+ * sgp4::rv2coe_SGP4, src/sgp4.cpp:2863-3064) for every state of a propagate result -- what the
+ * reference's verification printout does after each propagate (tests/test_perturb.cpp:385-397).
+ *   posvel  the six planes written by perturb_gpu_propagate (DEVICE memory, same strides)
+ *   coe     eleven planes coe[e * coe_plane_stride + i * row_stride + k] (DEVICE memory),
+ *           e = semilatus_rectum [km], semimajor_axis [km], eccentricity, inclination, raan,
+ *           arg_of_perigee, true_anomaly, mean_anomaly, arg_of_latitude, true_longitude,
+ *           longitude_of_periapsis [rad]: the member order of perturb::ClassicalOrbitalElements
+ *           (include/perturb/perturb.hpp:211-222). Elements the reference leaves "undefined"
+ *           carry its 999999.1 sentinel; states that are NaN (error codes 1-4) give NaN. */
+int perturb_gpu_rv2coe(const double *posvel, size_t n, size_t m, size_t row_stride,
+                       size_t plane_stride, int grav_model, double *coe,
+                       size_t coe_plane_stride, void *stream);
+
 int perturb_gpu_synchronize(perturb_gpu_batch *batch);
 
 /* ---- queries ------------------------------------------------------------------------- */

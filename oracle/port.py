@@ -71,6 +71,8 @@ def lib():
             C.POINTER(C.c_ubyte), dp]
         L.orc_propagate_grid_elems.restype = C.c_double
         L.orc_propagate_grid_elems.argtypes = L.orc_propagate_grid.argtypes + [dp]
+        L.orc_rv2coe.argtypes = [dp, dp, C.c_int, dp]
+        L.orc_rv2coe.restype = None
         L.orc_gstime.restype = C.c_double
         L.orc_gstime.argtypes = [C.c_double]
         _lib = L
@@ -194,3 +196,14 @@ class OracleSatellites:
             self.sats, self.n, _dp(ta), _dp(tb), m, int(bool(use_jd)), int(nthreads), None, None,
             err.ctypes.data_as(C.POINTER(C.c_int)), _dp(elems))
         return err, elems
+
+
+def rv2coe(r, v, grav=1):
+    """orc_rv2coe over states r, v [..., 3] -> [..., 11] (ClassicalOrbitalElements order)."""
+    r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((r.shape[0], 11))
+    L = lib()
+    for e in range(r.shape[0]):
+        L.orc_rv2coe(_dp(r[e]), _dp(v[e]), grav, _dp(out[e]))
+    return out

@@ -67,6 +67,8 @@ def lib():
         L.ref_propagate_grid.argtypes = [
             C.c_void_p, C.c_long, dp, dp, C.c_long, C.c_int, C.c_int, dp, dp,
             C.POINTER(C.c_int)]
+        L.ref_rv2coe.argtypes = [dp, dp, C.c_long, C.c_int, dp]
+        L.ref_rv2coe.restype = None
         _lib = L
     return _lib
 
@@ -203,3 +205,12 @@ def read_verif_file(path):
         l1.append(a)
         l2.append(b)
     return l1, l2
+
+
+def rv2coe(r, v, grav=1):
+    """ClassicalOrbitalElements(StateVector, grav) for states r, v [..., 3] -> [..., 11]."""
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros(r.shape[:-1] + (11,))
+    lib().ref_rv2coe(_dp(r), _dp(v), r.size // 3, grav, _dp(out))
+    return out

@@ -313,6 +313,31 @@ double ref_propagate_grid(
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// `ClassicalOrbitalElements(StateVector, GravModel)` (src/perturb.cpp:119-131) for `count`
+// states; r, v [count][3]; out [count][11] in the struct's member order.
+void ref_rv2coe(const double *r, const double *v, long count, int grav, double *out) {
+    for (long e = 0; e < count; ++e) {
+        StateVector sv;
+        for (int c = 0; c < 3; ++c) {
+            sv.position[c] = r[e * 3 + c];
+            sv.velocity[c] = v[e * 3 + c];
+        }
+        const perturb::ClassicalOrbitalElements coe(sv, to_grav(grav));
+        double *o = out + e * 11;
+        o[0] = coe.semilatus_rectum;
+        o[1] = coe.semimajor_axis;
+        o[2] = coe.eccentricity;
+        o[3] = coe.inclination;
+        o[4] = coe.raan;
+        o[5] = coe.arg_of_perigee;
+        o[6] = coe.true_anomaly;
+        o[7] = coe.mean_anomaly;
+        o[8] = coe.arg_of_latitude;
+        o[9] = coe.true_longitude;
+        o[10] = coe.longitude_of_periapsis;
+    }
+}
+
 int ref_hardware_threads(void) {
     const unsigned c = std::thread::hardware_concurrency();
     return c ? static_cast<int>(c) : 1;

@@ -1116,3 +1116,144 @@ static double grid_run(const orc_sat *sats, long n, const double *ta, const doub
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---------------------------------------------------------------------------------------
+ * rv2coe_SGP4 -- src/sgp4.cpp:2863-3064 (post-processing of a propagated state; "next" row
+ * N4 of SURVEY.md section 8f). Helpers: mag/dot/cross (:2564-2633), angle_SGP4 (:2659-2681),
+ * newtonnu_SGP4 (:2749-2803), asinh_SGP4 (:2705-2711).
+ * ------------------------------------------------------------------------------------- */
+static double vmag(const double x[3]) { return sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]); }
+static double vdot(const double x[3], const double y[3]) {
+    return (x[0] * y[0] + x[1] * y[1] + x[2] * y[2]);
+}
+static double vsgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
+
+static double vangle(const double a[3], const double b[3]) {
+    const double small = 0.00000001, undefined = 999999.1;
+    const double ma = vmag(a), mb = vmag(b);
+    if (ma * mb > small * small) {
+        double temp = vdot(a, b) / (ma * mb);
+        if (fabs(temp) > 1.0) temp = vsgn(temp) * 1.0;
+        return acos(temp);
+    }
+    return undefined;
+}
+
+static void kepler_from_true_anomaly(double ecc, double nu, double *e0, double *m) {
+    const double small = 0.00000001;
+    *e0 = 999999.9;
+    *m = 999999.9;
+    if (fabs(ecc) < small) {
+        *m = nu;
+        *e0 = nu;
+    } else if (ecc < 1.0 - small) {
+        const double sine = (sqrt(1.0 - ecc * ecc) * sin(nu)) / (1.0 + ecc * cos(nu));
+        const double cose = (ecc + cos(nu)) / (1.0 + ecc * cos(nu));
+        *e0 = atan2(sine, cose);
+        *m = *e0 - ecc * sin(*e0);
+    } else if (ecc > 1.0 + small) {
+        if ((ecc > 1.0) && (fabs(nu) + 0.00001 < PI - acos(1.0 / ecc))) {
+            const double sine = (sqrt(ecc * ecc - 1.0) * sin(nu)) / (1.0 + ecc * cos(nu));
+            *e0 = log(sine + sqrt(sine * sine + 1.0));
+            *m = ecc * sinh(*e0) - *e0;
+        }
+    } else if (fabs(nu) < 168.0 * PI / 180.0) {
+        *e0 = tan(nu * 0.5);
+        *m = *e0 + (*e0 * *e0 * *e0) / 3.0;
+    }
+    if (ecc < 1.0) {
+        *m = fmod(*m, 2.0 * PI);
+        if (*m < 0.0) *m = *m + 2.0 * PI;
+        *e0 = fmod(*e0, 2.0 * PI);
+    }
+}
+
+void orc_rv2coe(const double r[3], const double v[3], int grav, double out[11]) {
+    const double small = 0.00000001, undefined = 999999.1, infinite = 999999.9;
+    const double halfpi = 0.5 * PI;
+    orc_sat g;
+    orc_gravity(grav, &g);
+    const double mus = g.mus;
+    double p, a, ecc, incl, omega, argp, nu, m = 0.0, arglat, truelon, lonper;
+
+    const double magr = vmag(r), magv = vmag(v);
+    const double hbar[3] = {r[1] * v[2] - r[2] * v[1], r[2] * v[0] - r[0] * v[2],
+                            r[0] * v[1] - r[1] * v[0]};
+    const double magh = vmag(hbar);
+    if (magh > small) {
+        const double nbar[3] = {-hbar[1], hbar[0], 0.0};
+        const double magn = vmag(nbar);
+        const double c1 = magv * magv - mus / magr;
+        const double rdotv = vdot(r, v);
+        double ebar[3];
+        for (int i = 0; i <= 2; i++) ebar[i] = (c1 * r[i] - rdotv * v[i]) / mus;
+        ecc = vmag(ebar);
+        const double sme = (magv * magv * 0.5) - (mus / magr);
+        a = (fabs(sme) > small) ? -mus / (2.0 * sme) : infinite;
+        p = magh * magh / mus;
+        const double hk = hbar[2] / magh;
+        incl = acos(hk);
+
+        int orbit = 1; /* 1 'ei', 2 'ce', 3 'ci', 4 'ee' */
+        const int equatorial = (incl < small) | (fabs(incl - PI) < small);
+        if (ecc < small)
+            orbit = equatorial ? 2 : 3;
+        else if (equatorial)
+            orbit = 4;
+
+        if (magn > small) {
+            double temp = nbar[0] / magn;
+            if (fabs(temp) > 1.0) temp = vsgn(temp);
+            omega = acos(temp);
+            if (nbar[1] < 0.0) omega = TWOPI - omega;
+        } else
+            omega = undefined;
+
+        if (orbit == 1) {
+            argp = vangle(nbar, ebar);
+            if (ebar[2] < 0.0) argp = TWOPI - argp;
+        } else
+            argp = undefined;
+
+        if (orbit == 1 || orbit == 4) {
+            nu = vangle(ebar, r);
+            if (rdotv < 0.0) nu = TWOPI - nu;
+        } else
+            nu = undefined;
+
+        if (orbit == 3) {
+            arglat = vangle(nbar, r);
+            if (r[2] < 0.0) arglat = TWOPI - arglat;
+            m = arglat;
+        } else
+            arglat = undefined;
+
+        if (ecc > small && orbit == 4) {
+            double temp = ebar[0] / ecc;
+            if (fabs(temp) > 1.0) temp = vsgn(temp);
+            lonper = acos(temp);
+            if (ebar[1] < 0.0) lonper = TWOPI - lonper;
+            if (incl > halfpi) lonper = TWOPI - lonper;
+        } else
+            lonper = undefined;
+
+        if (magr > small && orbit == 2) {
+            double temp = r[0] / magr;
+            if (fabs(temp) > 1.0) temp = vsgn(temp);
+            truelon = acos(temp);
+            if (r[1] < 0.0) truelon = TWOPI - truelon;
+            if (incl > halfpi) truelon = TWOPI - truelon;
+            m = truelon;
+        } else
+            truelon = undefined;
+
+        if (orbit == 1 || orbit == 4) {
+            double e;
+            kepler_from_true_anomaly(ecc, nu, &e, &m);
+        }
+    } else {
+        p = a = ecc = incl = omega = argp = nu = m = arglat = truelon = lonper = undefined;
+    }
+    out[0] = p; out[1] = a; out[2] = ecc; out[3] = incl; out[4] = omega; out[5] = argp;
+    out[6] = nu; out[7] = m; out[8] = arglat; out[9] = truelon; out[10] = lonper;
+}

@@ -104,6 +104,11 @@ double orc_propagate_grid_elems(const orc_sat *sats, long n, const double *ta, c
                                 long m, int use_jd, int nthreads, double *pos, double *vel,
                                 int *err, double *elems);
 
+/* ClassicalOrbitalElements(StateVector, GravModel) -- src/perturb.cpp:119-131, i.e.
+ * rv2coe_SGP4 (src/sgp4.cpp:2863-3064) with newtonnu_SGP4 (:2749-2803) and angle_SGP4
+ * (:2659-2681). out[11] = p, a, ecc, incl, omega, argp, nu, m, arglat, truelon, lonper. */
+void orc_rv2coe(const double r[3], const double v[3], int grav, double out[11]);
+
 int orc_sizeof_sat(void);
 
 #ifdef __cplusplus

@@ -3,7 +3,7 @@
 `libperturb_gpu.so` (include/perturb_gpu.h); this package is its host-side Python mirror."""
 from . import capi  # noqa: F401
 from .batch import (  # noqa: F401
-    SatelliteBatch, block_to_lines, parse_tle_blocks, parse_tles, synth_catalog,
+    COE_NAMES, SatelliteBatch, block_to_lines, classical_elements, parse_tle_blocks, parse_tles, synth_catalog,
     synth_time_grid)
 from .sharding import (  # noqa: F401
     ShardedSatelliteBatch, estimate_class, max_over_ranks, plan_ranges, shard_blocks, shard_range)

@@ -82,6 +82,33 @@ def _ptr(x):
     return x.data_ptr()  # torch tensor
 
 
+COE_NAMES = (
+    "semilatus_rectum semimajor_axis eccentricity inclination raan arg_of_perigee "
+    "true_anomaly mean_anomaly arg_of_latitude true_longitude longitude_of_periapsis").split()
+
+
+def classical_elements(posvel, grav=capi.WGS72):
+    """Batched `ClassicalOrbitalElements(sv, grav)`: posvel [6, n, m] (numpy or torch CUDA)
+    -> coe [11, n, m] torch CUDA tensor, planes in COE_NAMES order."""
+    import torch
+    pv = torch.as_tensor(posvel, dtype=torch.float64)
+    if not pv.is_cuda:
+        pv = pv.cuda()
+    if pv.stride(2) != 1:
+        pv = pv.contiguous()
+    _, n, m = pv.shape
+    row, plane = pv.stride(1), pv.stride(0)
+    if n <= 1:
+        row = max(row, m)
+    plane = max(plane, n * row)
+    coe = torch.empty((11, n, row), dtype=torch.float64, device=pv.device)
+    st = capi.lib().perturb_gpu_rv2coe(pv.data_ptr(), n, m, row, plane, int(grav),
+                                       coe.data_ptr(), n * row, None)
+    capi.check(st, "perturb_gpu_rv2coe")
+    torch.cuda.synchronize(pv.device)
+    return coe[:, :, :m]
+
+
 class SatelliteBatch:
     def __init__(self, handle, n):
         self._h = handle

@@ -93,6 +93,10 @@ def main():
         fresh = ref.RefSatellites.from_verif(l1, l2, ops)
         out["walk_" + ops] = walk(fresh, grids)
     out["grids"] = np.array(grids)
+    # ClassicalOrbitalElements of every written state of the full grids (opsmode 'a')
+    rows = out["full_a"]
+    ok = np.isin(rows[:, 2].astype(int), (0, 6))
+    out["coe_a"] = ref.rv2coe(rows[ok, 3:6], rows[ok, 6:9])
 
     # public-API route, opsmode 'i': Satellite::from_tle, then propagate(JulianDate)
     pub = ref.RefSatellites.from_tle_lines(l1s, l2s)

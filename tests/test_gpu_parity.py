@@ -306,6 +306,59 @@ def test_mean_element_side_outputs(use_jd):
     assert np.abs(g[:, 6] / o[:, 6] - 1.0).max() < 1e-11
 
 
+# ---- N4: classical orbital elements of the propagated states -----------------------------------
+def test_classical_elements_batch():
+    """perturb_gpu_rv2coe against the oracle's rv2coe on the GPU's own states (so only
+    libdevice-vs-glibc acos/atan2/sin differ), incl. sentinel / NaN patterns."""
+    l1, l2 = ver_lines(G)
+    n = 1500
+    b1, b2 = pb.synth_catalog(3, n, seed=3)
+    L1 = l1 + pb.block_to_lines(b1, n)
+    L2 = l2 + pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    mins = np.linspace(-720.0, 4320.0, 43)
+    pv, err = b.propagate_from_epoch(mins)
+    coe = pb.classical_elements(pv).cpu().numpy()
+    pos, vel = posvel_to_rv(pv)
+    written = np.isin(err, (0, 6))
+    assert np.isnan(coe[:, ~written]).all() and np.isfinite(coe[:, written]).all()
+    want = port.rv2coe(pos[written], vel[written])
+    got = np.moveaxis(coe, 0, -1)[written]
+    # the 999999.1 "undefined" / 999999.9 "infinite" sentinels sit in exactly the same places
+    sent_w = want > 9.0e5
+    assert np.array_equal(got > 9.0e5, sent_w)
+    assert np.array_equal(got[sent_w], want[sent_w])
+    val = ~sent_w
+    ecc = want[:, 2]
+    # p, a: relative; ecc, incl: absolute; the anomalies lose accuracy like 1/ecc (and raan
+    # like 1/sin(incl)) in any implementation -- acos near +-1 -- so scale the bar with them
+    assert np.abs(got[:, 0] / want[:, 0] - 1.0).max() < 1e-12
+    assert np.abs(got[:, 1] / want[:, 1] - 1.0).max() < 1e-11
+    assert np.abs(got[:, 2] - want[:, 2]).max() < 1e-13
+    assert np.abs(got[:, 3] - want[:, 3]).max() < 1e-9
+    def angdiff(j):
+        ok = val[:, j]
+        return np.abs((got[ok, j] - want[ok, j] + np.pi) % (2 * np.pi) - np.pi), ok
+    d, ok = angdiff(4)
+    assert (d * np.sin(want[ok, 3]) < 1e-9).all()
+    for j in (5, 6, 7):
+        d, ok = angdiff(j)
+        assert (d * np.maximum(ecc[ok], 1e-7) < 1e-9).all(), COE_J[j]
+    # and the golden values of the reference itself on the verification states
+    r, v = G["full_a"][:, 3:6], G["full_a"][:, 6:9]
+    okrow = np.isin(G["full_a"][:, 2].astype(int), (0, 6))
+    pvg = np.ascontiguousarray(np.concatenate([r[okrow].T, v[okrow].T])[:, None, :])
+    cg = np.moveaxis(pb.classical_elements(pvg).cpu().numpy(), 0, -1)[0]
+    ref_coe = G["coe_a"]
+    assert np.array_equal(cg > 9.0e5, ref_coe > 9.0e5)
+    reg = (ref_coe[:, 2] > 1e-3) & (ref_coe[:, 2] < 0.99) & (ref_coe[:, 1] > 0)
+    assert np.abs(cg[reg, 1] / ref_coe[reg, 1] - 1.0).max() < 1e-10
+    assert np.abs(cg[reg, 2] - ref_coe[reg, 2]).max() < 1e-12
+
+
+COE_J = pb.COE_NAMES
+
+
 # ---- N1: TLE text parsed on the device ------------------------------------------------------
 @pytest.mark.parametrize("flavor", [0, 1])
 def test_device_tle_parser_equals_host_parser(flavor):

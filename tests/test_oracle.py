@@ -181,3 +181,42 @@ def test_oracle_equals_compiled_reference_live():
         er, pr, vr, _ = R0.propagate_grid(jd[sel], fr[sel], use_jd=True)
         eo, po, vo, _ = O0.propagate_grid(jd[sel], fr[sel], use_jd=True)
         assert np.array_equal(er, eo) and _same(pr, po) and _same(vr, vo)
+
+
+def _golden_states(ops="a"):
+    rows = G["full_" + ops]
+    ok = np.isin(rows[:, 2].astype(int), (0, 6))
+    return rows[ok, 3:6], rows[ok, 6:9]
+
+
+def test_oracle_rv2coe_matches_golden():
+    """rv2coe_SGP4 on every state of the verification grids (the reference's printout path)."""
+    r, v = _golden_states()
+    got = port.rv2coe(r, v)
+    assert _same(got, G["coe_a"])
+    assert (got[:, 3] >= 0).all() and (got[:, 3] <= np.pi).all()
+    assert (got[:, 2] > 1.0).any()  # the decayed / garbage states exercise the hyperbolic branch
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference)")
+def test_oracle_rv2coe_equals_compiled_reference_on_special_orbits():
+    """Circular / equatorial / hyperbolic / degenerate branches with their 999999.1 sentinels."""
+    mu = 398600.8
+    rc = 7000.0
+    vc = np.sqrt(mu / rc)
+    cases = [
+        ([rc, 0, 0], [0, vc, 0]),                 # circular equatorial
+        ([rc, 0, 0], [0, vc * 0.6, vc * 0.8]),    # circular inclined
+        ([rc, 0, 0], [0, vc * 1.2, 0]),           # elliptical equatorial
+        ([rc, 0, 0], [0, -vc * 1.2, 0]),          # retrograde equatorial
+        ([rc, 0, 0], [1.0, vc * 1.1, 2.0]),       # generic elliptical
+        ([rc, 0, 0], [0.5, vc * 1.6, 1.0]),       # hyperbolic
+        ([rc, 0, 0], [0, vc * np.sqrt(2.0), 0]),  # parabolic
+        ([rc, 0, 0], [3.0, 0, 0]),                # rectilinear: h = 0 -> all undefined
+        ([0, 0, rc], [vc, 0, 0]),                 # polar
+    ]
+    r = np.array([c[0] for c in cases], dtype=float)
+    v = np.array([c[1] for c in cases], dtype=float)
+    for grav in (0, 1, 2):
+        assert _same(port.rv2coe(r, v, grav), ref.rv2coe(r, v, grav))
+    assert (port.rv2coe(r, v)[7] == 999999.1).all()
