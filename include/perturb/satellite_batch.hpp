@@ -59,14 +59,17 @@ public:
             lines_1[i].copy(&b1[i * STRIDE], STRIDE - 1);
             lines_2[i].copy(&b2[i * STRIDE], STRIDE - 1);
         }
-        std::vector<perturb_gpu_tle> packed(n);
         SatelliteBatch batch;
         batch.n_ = n;
-        batch.status_ = perturb_gpu_parse_tles(
-            b1.data(), b2.data(), STRIDE, n, 1, packed.data(), nullptr
+        batch.init_error_.assign(n, static_cast<std::int32_t>(Sgp4Error::UNKNOWN));
+        // TLE text is parsed on the device (flavor 1 = twoline2rv's numeric conventions),
+        // 'i' = the opsmode Satellite::from_tle hard-wires (perturb.cpp:200)
+        batch.status_ = perturb_gpu_init_from_text(
+            b1.data(), b2.data(), STRIDE, n, 1, grav_code(grav_model), 'i', device,
+            &batch.handle_, batch.init_error_.data(), nullptr
         );
         if (batch.status_ == PERTURB_GPU_OK) {
-            batch.init(packed, grav_model, device);
+            batch.fetch_queries();
         }
         return batch;
     }
@@ -217,6 +220,10 @@ private:
         if (status_ != PERTURB_GPU_OK) {
             return;
         }
+        fetch_queries();
+    }
+
+    void fetch_queries() {
         status_ = perturb_gpu_last_error(handle_, init_error_.data());
         epoch_jd_.assign(n_, 0.0);
         epoch_frac_.assign(n_, 0.0);
