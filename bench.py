@@ -342,6 +342,19 @@ def run_gpu(args):
         _ = int(h_err[0, 0])
     e2e_s = time.perf_counter() - te
     e2e_value = float(n) * me * world * e2e_steps / pb.max_over_ranks(e2e_s, dist, dev)
+    # ---- the fused consumer (N3): host time grid in, one 40-byte summary per satellite out ----
+    hs_jd = torch.tensor(jd).pin_memory()
+    hs_fr = torch.tensor(fr).pin_memory()
+    summ = batch.propagate_summary(hs_jd, hs_fr)  # warm-up: allocates the partials scratch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ts = time.perf_counter()
+    for _ in range(e2e_steps):
+        summ = batch.propagate_summary(hs_jd, hs_fr)  # synchronises: summaries are on the host
+    sum_s = time.perf_counter() - ts
+    sum_value = float(n) * m * world * e2e_steps / pb.max_over_ranks(sum_s, dist, dev)
+    sum_launches = batch.last_launch_count()
     os.sched_setaffinity(0, all_cpus)  # the CPU arm below uses every host core again
     codes_ok = float((h_err == 0).double().mean())
 
@@ -422,6 +435,17 @@ def run_gpu(args):
             "steps": e2e_steps,
             "host_buffers": "pinned",
             "placement": numa,
+        },
+        "e2e_summary": {
+            "value": sum_value,
+            "unit": "evals/s",
+            "what": "perturb_gpu_propagate_summary, host time grid in / host per-satellite "
+                    "summaries out, full grid; wall clock incl. copies and synchronisation",
+            "h2d_bytes_per_step": int(2 * m * 8),
+            "d2h_bytes_per_step": int(n * 40),
+            "steps": e2e_steps,
+            "launches_per_step": int(sum_launches),
+            "ok_fraction": float(summ["n_ok"].sum()) / (float(n) * m),
         },
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,

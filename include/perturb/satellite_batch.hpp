@@ -182,6 +182,21 @@ public:
         return status_;
     }
 
+    /// Fused consumer: per-satellite envelope (min / max |position|, count of NONE results,
+    /// first error and where) of `sat.propagate(times[k], sv)` over the whole grid, without
+    /// materialising the states. `out` [size()], host or device memory; `jd_frac == nullptr`
+    /// selects the propagate_from_epoch form with `jd` = minutes.
+    int propagate_summary(
+        const double *jd, const double *jd_frac, std::size_t m, perturb_gpu_summary *out,
+        void *stream
+    ) {
+        status_ = perturb_gpu_propagate_summary(handle_, jd, jd_frac, m, out, stream);
+        if (status_ == PERTURB_GPU_OK && stream == nullptr) {
+            status_ = perturb_gpu_synchronize(handle_);
+        }
+        return status_;
+    }
+
     perturb_gpu_batch *handle() { return handle_; }
 
 private:

@@ -148,6 +148,32 @@ int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
                                    int32_t *err, double *elements, size_t row_stride,
                                    size_t plane_stride, void *stream);
 
+/* Fused consumer: per-satellite summary of a propagation computed on the
+ * fly -- nothing of size [n][m] is written, which removes the 52 B/evaluation output (and the
+ * PCIe transfer behind it) for screens that only need an envelope. Equivalent to running
+ * `sat.propagate(t_k, sv)` for k = 0..m-1 and keeping, per satellite:
+ *   r_min, k_min   smallest |sv.position| [km] over evaluations that returned NONE, and the
+ *                  lowest k attaining it (r_min = +inf, k_min = -1 if there is none)
+ *   r_max, k_max   largest |sv.position| likewise (r_max = -inf, k_max = -1 if none)
+ *   n_ok           number of evaluations that returned NONE
+ *   first_error    Sgp4Error of the lowest k that did not return NONE (0 if all did), and
+ *   k_first_error  that k (-1 if none) -- where the reference's verification loop would stop
+ *                  (tests/test_perturb.cpp:368-373)
+ * jd_frac == NULL selects the `propagate_from_epoch` form with `jd` holding minutes.
+ * `out` [n] may be host or device memory, satellites in caller order. */
+typedef struct perturb_gpu_summary {
+    double r_min, r_max;
+    int32_t k_min, k_max;
+    int32_t n_ok;
+    int32_t first_error;
+    int32_t k_first_error;
+    int32_t reserved;
+} perturb_gpu_summary;
+
+int perturb_gpu_propagate_summary(perturb_gpu_batch *batch, const double *jd,
+                                  const double *jd_frac, size_t m, perturb_gpu_summary *out,
+                                  void *stream);
+
 /* Replaces `ClassicalOrbitalElements(StateVector, GravModel)` (src/perturb.cpp:119-131, i.e.
  * sgp4::rv2coe_SGP4, src/sgp4.cpp:2863-3064) for every state of a propagate result -- what the
  * reference's verification printout does after each propagate (tests/test_perturb.cpp:385-397).

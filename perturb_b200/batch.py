@@ -287,6 +287,29 @@ class SatelliteBatch:
         self.synchronize()
         return posvel, err, elements
 
+    SUMMARY_DTYPE = np.dtype([("r_min", "f8"), ("r_max", "f8"), ("k_min", "i4"), ("k_max", "i4"),
+                              ("n_ok", "i4"), ("first_error", "i4"), ("k_first_error", "i4"),
+                              ("reserved", "i4")])
+
+    def propagate_summary(self, jd, jd_frac=None, stream=None):
+        """Fused consumer: per-satellite envelope of a propagation (numpy structured array [n],
+        SUMMARY_DTYPE) without materialising the [n, m] states. jd_frac None: jd = minutes."""
+        out = np.zeros(self.n, dtype=self.SUMMARY_DTYPE)
+        assert out.dtype.itemsize == C.sizeof(capi.Summary)
+        st = capi.lib().perturb_gpu_propagate_summary(
+            self._h, _ptr(jd), _ptr(jd_frac), int(jd.shape[0]), out.ctypes.data, stream)
+        capi.check(st, "perturb_gpu_propagate_summary")
+        self.synchronize()
+        return out
+
+    def propagate_summary_device(self, jd, jd_frac, out, stream=None):
+        """Same with a device-resident result: `out` is a CUDA torch.uint8 tensor of
+        n * SUMMARY_DTYPE.itemsize bytes; asynchronous on `stream`."""
+        assert out.is_cuda and out.numel() * out.element_size() >= self.n * self.SUMMARY_DTYPE.itemsize
+        st = capi.lib().perturb_gpu_propagate_summary(
+            self._h, _ptr(jd), _ptr(jd_frac), int(jd.shape[0]), out.data_ptr(), stream)
+        capi.check(st, "perturb_gpu_propagate_summary")
+
     def propagate_from_epoch(self, mins, posvel=None, err=None, stream=None, sync=True):
         m = int(mins.shape[0])
         posvel, err = self._outputs(m, posvel, err)

@@ -28,7 +28,7 @@ class Tle(C.Structure):
 # Every symbol include/perturb_gpu.h and include/perturb_synth.h declare.
 EXPORTS = (
     "perturb_gpu_init perturb_gpu_init_from_text perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
-    "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_elements perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_size "
+    "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_elements perturb_gpu_propagate_summary perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_size "
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles "
@@ -37,6 +37,13 @@ EXPORTS = (
 ).split()
 
 _lib = None
+
+
+class Summary(C.Structure):
+    """perturb_gpu_summary"""
+    _fields_ = [("r_min", C.c_double), ("r_max", C.c_double), ("k_min", C.c_int32),
+                ("k_max", C.c_int32), ("n_ok", C.c_int32), ("first_error", C.c_int32),
+                ("k_first_error", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PerturbGpuError(RuntimeError):
@@ -66,6 +73,7 @@ def lib():
         vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_size_t, vp]
     L.perturb_gpu_propagate_elements.argtypes = [
         vp, vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_size_t, vp]
+    L.perturb_gpu_propagate_summary.argtypes = [vp, vp, vp, C.c_size_t, vp, vp]
     L.perturb_gpu_rv2coe.argtypes = [
         vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, vp]
     L.perturb_gpu_synchronize.argtypes = [vp]

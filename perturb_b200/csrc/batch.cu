@@ -126,12 +126,14 @@ struct perturb_gpu_batch {
     cudaStream_t aux[PB_CLS_COUNT];  // forked streams, one per orbit class
     cudaEvent_t ev_fork, ev_join[PB_CLS_COUNT];
     int last_launches;
+    void *d_summary;  // scratch of perturb_gpu_propagate_summary
+    size_t summary_cap;
 
     perturb_gpu_batch()
         : device(0), n(0), n_pad(0), opsmode_a(false), d_rec(nullptr), d_pf(nullptr),
           d_perm(nullptr), stream(nullptr), last_stream(nullptr), copy_stream(nullptr),
           d_times(nullptr),
-          times_cap(0), last_launches(0) {
+          times_cap(0), last_launches(0), d_summary(nullptr), summary_cap(0) {
         for (int c = 0; c < PB_CLS_COUNT; ++c) {
             tile_begin[c] = tile_count[c] = 0;
             aux[c] = nullptr;
@@ -172,6 +174,7 @@ void destroy(perturb_gpu_batch *b) {
         if (b->ev_join[c]) cudaEventDestroy(b->ev_join[c]);
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    cudaFree(b->d_summary);
     cudaFree(b->d_res_nodes);
     cudaFree(b->d_res_k0);
     cudaFree(b->d_res_cnt);
@@ -486,6 +489,9 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     fill_launch(b, l);
     l.use_jd = use_jd ? 1 : 0;
     l.elements = elements;
+    l.summary_partials = nullptr;
+    l.summary_out = nullptr;
+    l.n = b->n;
     if (elements != nullptr && !(is_device_pointer(elements) && is_device_pointer(posvel) &&
                                  is_device_pointer(err))) {
         return fail(PERTURB_GPU_ERR_ARG, "propagate_elements needs device output buffers");
@@ -636,6 +642,73 @@ int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
     if (elements == nullptr) return fail(PERTURB_GPU_ERR_ARG, "elements is null");
     return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m, posvel, err, row_stride,
                           plane_stride, stream, elements);
+}
+
+int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const double *jd_frac,
+                                  size_t m, perturb_gpu_summary *out, void *stream_arg) {
+    if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    b->last_launches = 0;
+    if (b->n == 0) return PERTURB_GPU_OK;
+    if (jd == nullptr || out == nullptr || m == 0 || m > (static_cast<size_t>(1) << 30)) {
+        return fail(PERTURB_GPU_ERR_ARG, "null pointer or empty / oversized time grid");
+    }
+    const bool use_jd = jd_frac != nullptr;
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_arg);
+    b->last_stream = stream;
+
+    const double *d_ta = jd, *d_tb = jd_frac;
+    const bool ta_dev = is_device_pointer(jd);
+    const bool tb_dev = use_jd ? is_device_pointer(jd_frac) : true;
+    if (!ta_dev || !tb_dev) {
+        int st = ensure_times(b, m);
+        if (st != PERTURB_GPU_OK) return st;
+        if (!ta_dev) {
+            PB_CUDA(cudaMemcpyAsync(b->d_times, jd, m * sizeof(double), cudaMemcpyHostToDevice,
+                                    stream));
+            d_ta = b->d_times;
+        }
+        if (use_jd && !tb_dev) {
+            PB_CUDA(cudaMemcpyAsync(b->d_times + m, jd_frac, m * sizeof(double),
+                                    cudaMemcpyHostToDevice, stream));
+            d_tb = b->d_times + m;
+        }
+    }
+    // scratch: partial records [n][chunks] + (for host output) the folded records [n]
+    const size_t chunks = pb::summary_chunks(m);
+    const size_t need = (b->n * chunks + b->n) * sizeof(perturb_gpu_summary);
+    if (b->summary_cap < need) {
+        cudaFree(b->d_summary);
+        b->d_summary = nullptr;
+        b->summary_cap = 0;
+        PB_CUDA(cudaMalloc(&b->d_summary, need));
+        b->summary_cap = need;
+    }
+    perturb_gpu_summary *partials = static_cast<perturb_gpu_summary *>(b->d_summary);
+    perturb_gpu_summary *folded = partials + b->n * chunks;
+    const bool out_dev = is_device_pointer(out);
+
+    pb::PropLaunch l;
+    fill_launch(b, l);
+    l.use_jd = use_jd ? 1 : 0;
+    l.ta = d_ta;
+    l.tb = d_tb;
+    l.m = static_cast<int>(m);
+    l.out = nullptr;
+    l.err = nullptr;
+    l.plane_stride = l.row_stride = l.err_row_stride = 0;
+    l.elements = nullptr;
+    l.summary_partials = partials;
+    l.summary_out = out_dev ? out : folded;
+    l.n = b->n;
+    b->last_launches = pb::launch_sgp4_propagate(l, stream);
+    PB_CUDA(cudaGetLastError());
+    if (!out_dev) {
+        PB_CUDA(cudaMemcpyAsync(out, folded, b->n * sizeof(perturb_gpu_summary),
+                                cudaMemcpyDeviceToHost, stream));
+    }
+    return PERTURB_GPU_OK;
 }
 
 int perturb_gpu_synchronize(perturb_gpu_batch *batch) {

@@ -52,6 +52,10 @@ struct PropLaunch {
     int32_t *err;  // err[sat * err_row_stride + k]
     size_t err_row_stride;
     double *elements;  // optional 7 planes am, em, im, Om, om, mm, nm (same strides as out)
+    // fused summary mode (out/err unused): partials [n][chunks], then summary [n]
+    void *summary_partials;  // perturb_gpu_summary [n * summary_chunks], scratch
+    void *summary_out;       // perturb_gpu_summary [n]
+    size_t n;                // satellites (caller count), needed by the reduce pass
     double radiusearthkm, xke, j2, j3oj2;
     int opsmode_a;
     // resonance node table scratch (null / 0: resonant evaluations integrate in-line)
@@ -67,6 +71,9 @@ struct PropLaunch {
 
 // Kernel 2, one launch per non-empty class. Returns the number of launches issued.
 int launch_sgp4_propagate(const PropLaunch &p, cudaStream_t stream);
+
+// Number of per-satellite partial records the summary mode needs for a grid of m times.
+size_t summary_chunks(size_t m);
 
 }  // namespace pb
 

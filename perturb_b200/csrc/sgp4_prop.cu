@@ -12,6 +12,7 @@
 //     into the caller-order row (the sort permutation costs nothing on output);
 //   * each lane evaluates TPL = 2 times per satellite (l and l + 32 of the warp's 64).
 // FP64 pipe bound; no tensor cores (not a contraction).
+#include "../../include/perturb_gpu.h"
 #include "batch_internal.h"
 #include "sgp4_eval.cuh"
 
@@ -76,6 +77,8 @@ struct PropParams {
     int32_t *err;
     size_t err_row_stride;
     double *elements;
+    perturb_gpu_summary *partials;  // summary mode: [sat * chunks + chunk]
+    int chunks;
     GravConsts g;
     int opsmode_a;
     // resonance node table (deep-space resonant classes only)
@@ -197,9 +200,38 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     }
 }
 
-template <int CLS, bool WANT_ELEMENTS>
+// Output modes of kernel 2
+constexpr int kModeStates = 0;    // six state planes + error plane
+constexpr int kModeElements = 1;  // ... plus the seven mean-element planes
+constexpr int kModeSummary = 2;   // fused consumer: per-satellite envelope, no [n][m] output
+
+struct LaneSummary {
+    double r_min, r_max;
+    int k_min, k_max, n_ok, k_err, code_err;
+};
+
+// Combine two partial summaries; `b` covers later times than `a` only in the sense that ties
+// go to the lower time index, which the explicit index comparisons implement.
+__device__ __forceinline__ void merge_summary(LaneSummary &a, const LaneSummary &b) {
+    if (b.r_min < a.r_min || (b.r_min == a.r_min && b.k_min >= 0 && (a.k_min < 0 || b.k_min < a.k_min))) {
+        a.r_min = b.r_min;
+        a.k_min = b.k_min;
+    }
+    if (b.r_max > a.r_max || (b.r_max == a.r_max && b.k_max >= 0 && (a.k_max < 0 || b.k_max < a.k_max))) {
+        a.r_max = b.r_max;
+        a.k_max = b.k_max;
+    }
+    a.n_ok += b.n_ok;
+    if (b.k_err >= 0 && (a.k_err < 0 || b.k_err < a.k_err)) {
+        a.k_err = b.k_err;
+        a.code_err = b.code_err;
+    }
+}
+
+template <int CLS, int MODE>
 __global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR : PB_MIN_BLOCKS_DEEP)
 sgp4_prop_kernel(const PropParams p) {
+    constexpr bool WANT_ELEMENTS = (MODE == kModeElements);
     using TF = TileFields<CLS>;
     __shared__ double s_pf[TF::kRows * PB_TILE_SATS];
     __shared__ double s_ta[kTimeTile];
@@ -263,8 +295,10 @@ sgp4_prop_kernel(const PropParams p) {
             nodes.k0 = s_k0[s];
             nodes.count = s_cnt[s];
         }
-        double *row = p.out + static_cast<size_t>(dst) * p.row_stride;
-        int32_t *erow = p.err + static_cast<size_t>(dst) * p.err_row_stride;
+        double *row = (MODE == kModeSummary) ? nullptr : p.out + static_cast<size_t>(dst) * p.row_stride;
+        int32_t *erow = (MODE == kModeSummary) ? nullptr : p.err + static_cast<size_t>(dst) * p.err_row_stride;
+        LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
+                           __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
 
         // The two evaluations share ONE copy of the code (a rolled loop): the body is ~15 KB
         // of SASS and the instruction cache is 32 KB.
@@ -290,7 +324,19 @@ sgp4_prop_kernel(const PropParams p) {
                 erow_el[5 * p.plane_stride] = stored ? side.mm : nan;
                 erow_el[6 * p.plane_stride] = stored ? side.nm : nan;
             }
-            if (kt < p.m) {
+            if (MODE == kModeSummary) {
+                if (kt < p.m) {
+                    if (cd == 0) {
+                        const double rr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                        if (rr < acc.r_min) { acc.r_min = rr; acc.k_min = kt; }
+                        if (rr > acc.r_max) { acc.r_max = rr; acc.k_max = kt; }
+                        acc.n_ok += 1;
+                    } else if (acc.k_err < 0) {
+                        acc.k_err = kt;  // j = 0 precedes j = 1 in time
+                        acc.code_err = cd;
+                    }
+                }
+            } else if (kt < p.m) {
                 // codes 1-4: the reference leaves the caller's state untouched -> NaN
                 const bool written = (cd == 0) || (cd == 6);
 #pragma unroll
@@ -300,7 +346,60 @@ sgp4_prop_kernel(const PropParams p) {
                 erow[kt] = cd;
             }
         }
+        if (MODE == kModeSummary) {
+            // warp reduction over the 64 times of this satellite, then one partial record
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                LaneSummary o;
+                o.r_min = __shfl_down_sync(0xffffffffu, acc.r_min, off);
+                o.r_max = __shfl_down_sync(0xffffffffu, acc.r_max, off);
+                o.k_min = __shfl_down_sync(0xffffffffu, acc.k_min, off);
+                o.k_max = __shfl_down_sync(0xffffffffu, acc.k_max, off);
+                o.n_ok = __shfl_down_sync(0xffffffffu, acc.n_ok, off);
+                o.k_err = __shfl_down_sync(0xffffffffu, acc.k_err, off);
+                o.code_err = __shfl_down_sync(0xffffffffu, acc.code_err, off);
+                merge_summary(acc, o);
+            }
+            if (lane == 0) {
+                perturb_gpu_summary out;
+                out.r_min = acc.r_min;
+                out.r_max = acc.r_max;
+                out.k_min = acc.k_min;
+                out.k_max = acc.k_max;
+                out.n_ok = acc.n_ok;
+                out.first_error = acc.code_err;
+                out.k_first_error = acc.k_err;
+                out.reserved = 0;
+                p.partials[static_cast<size_t>(dst) * p.chunks + (ttile * kWarps + warp)] = out;
+            }
+        }
     }
+}
+
+// Second pass of the summary mode: one thread per satellite folds its chunk partials.
+__global__ void __launch_bounds__(128)
+summary_reduce_kernel(const perturb_gpu_summary *__restrict__ partials, int chunks, int used_chunks,
+                      size_t n, perturb_gpu_summary *__restrict__ out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
+                       __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
+    for (int c = 0; c < used_chunks; ++c) {
+        const perturb_gpu_summary q = partials[i * chunks + c];
+        const LaneSummary o = {q.r_min, q.r_max, q.k_min, q.k_max, q.n_ok, q.k_first_error,
+                               q.first_error};
+        merge_summary(acc, o);
+    }
+    perturb_gpu_summary r;
+    r.r_min = acc.r_min;
+    r.r_max = acc.r_max;
+    r.k_min = acc.k_min;
+    r.k_max = acc.k_max;
+    r.n_ok = acc.n_ok;
+    r.first_error = acc.code_err;
+    r.k_first_error = acc.k_err;
+    r.reserved = 0;
+    out[i] = r;
 }
 
 template <int CLS>
@@ -316,10 +415,12 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
         stream = l.aux[CLS];
         cudaStreamWaitEvent(stream, l.fork, 0);
     }
-    if (p.elements != nullptr) {
-        sgp4_prop_kernel<CLS, true><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    if (p.partials != nullptr) {
+        sgp4_prop_kernel<CLS, kModeSummary><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    } else if (p.elements != nullptr) {
+        sgp4_prop_kernel<CLS, kModeElements><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     } else {
-        sgp4_prop_kernel<CLS, false><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+        sgp4_prop_kernel<CLS, kModeStates><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     }
     if (forked) {
         cudaEventRecord(l.join[CLS], stream);
@@ -329,6 +430,10 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
 }
 
 }  // namespace
+
+size_t summary_chunks(size_t m) {
+    return ((m + kTimeTile - 1) / kTimeTile) * kWarps;
+}
 
 int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     if (l.m <= 0) return 0;
@@ -348,6 +453,8 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.err = l.err;
     p.err_row_stride = l.err_row_stride;
     p.elements = l.elements;
+    p.partials = static_cast<perturb_gpu_summary *>(l.summary_partials);
+    p.chunks = static_cast<int>(summary_chunks(static_cast<size_t>(l.m)));
     p.g.radiusearthkm = l.radiusearthkm;
     p.g.xke = l.xke;
     p.g.j2 = l.j2;
@@ -385,6 +492,14 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     launch_class<PB_CLS_DEEP_NR>(l, p, stream, launches);
     launch_class<PB_CLS_NEAR_FULL>(l, p, stream, launches);
     launch_class<PB_CLS_NEAR_SIMP>(l, p, stream, launches);
+    if (l.summary_partials != nullptr && l.summary_out != nullptr && l.n > 0) {
+        // every (satellite, chunk) partial with chunk * 64 < m has been written by exactly one
+        // warp of exactly one class launch; all of them were joined back into `stream`
+        const int used = static_cast<int>((static_cast<size_t>(l.m) + 32 * kTpl - 1) / (32 * kTpl));
+        summary_reduce_kernel<<<static_cast<unsigned>((l.n + 127) / 128), 128, 0, stream>>>(
+            p.partials, p.chunks, used, l.n, static_cast<perturb_gpu_summary *>(l.summary_out));
+        ++launches;
+    }
     return launches + prelaunches;
 }
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import perturb_b200 as pb
-from helpers import (ISS_1, ISS_2, compare_states, load_synth_golden, load_ver_golden,
+from helpers import (ISS_1, ISS_2, SENS_GAIN, TOL_POS_KM, compare_states, load_synth_golden, load_ver_golden,
                      oracle_sensitivity_jd, oracle_sensitivity_mins, posvel_to_rv, ver_lines)
 from oracle import port
 
@@ -304,6 +304,104 @@ def test_mean_element_side_outputs(use_jd):
         same_branch = np.abs(g[:, j] - o[:, j]) < 1e-9
         assert same_branch.mean() > 0.999, name  # C fmod representative, not just mod 2 pi
     assert np.abs(g[:, 6] / o[:, 6] - 1.0).max() < 1e-11
+
+
+# ---- N3: fused per-satellite summary (no [n, m] output) -----------------------------------------
+def _summary_of(err, pos):
+    """numpy statement of perturb_gpu_summary from a full propagation (err [n,m], pos [n,m,3])."""
+    n, m = err.shape
+    r = np.sqrt((pos ** 2).sum(-1))
+    ok = err == 0
+    out = np.zeros(n, dtype=pb.SatelliteBatch.SUMMARY_DTYPE)
+    rlo = np.where(ok, r, np.inf)
+    rhi = np.where(ok, r, -np.inf)
+    any_ok = ok.any(1)
+    out["r_min"], out["r_max"] = rlo.min(1), rhi.max(1)
+    out["k_min"] = np.where(any_ok, rlo.argmin(1), -1)  # argmin/argmax: first occurrence
+    out["k_max"] = np.where(any_ok, rhi.argmax(1), -1)
+    out["n_ok"] = ok.sum(1)
+    bad = ~ok
+    kf = np.where(bad.any(1), bad.argmax(1), -1)
+    out["k_first_error"] = kf
+    out["first_error"] = np.where(kf >= 0, err[np.arange(n), np.maximum(kf, 0)], 0)
+    return out, r
+
+
+@pytest.mark.parametrize("use_jd,m", [(True, 777), (False, 64), (False, 1)])
+def test_fused_summary_matches_a_reduction_of_the_full_propagation(use_jd, m):
+    """perturb_gpu_propagate_summary == reducing what Satellite::propagate returns over the grid
+    (the verification loop's stop-at-first-error, tests/test_perturb.cpp:368-373, plus the
+    |r| envelope), checked against the oracle and, bit-tight, against the GPU's own full output."""
+    l1, l2 = ver_lines(G)
+    n = 2100
+    b1, b2 = pb.synth_catalog(3, n, seed=23)
+    L1 = l1 + pb.block_to_lines(b1, n)
+    L2 = l2 + pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, "i", flavor=1)
+    if use_jd:
+        jd, fr = pb.synth_time_grid(10080)
+        sel = np.linspace(0, 10079, m).astype(int)
+        ta, tb = jd[sel], fr[sel]
+        sr, _ = oracle_sensitivity_jd(orc, ta, tb)
+        pv, err = b.propagate(ta, tb)
+    else:
+        ta, tb = np.linspace(-720.0, 30000.0, m), None
+        sr, _ = oracle_sensitivity_mins(orc, ta)
+        pv, err = b.propagate_from_epoch(ta)
+    s = b.propagate_summary(ta, tb)
+    assert s.shape == (b.n,) and (s["reserved"] == 0).all()
+
+    # (1) against the GPU's own full propagation: integer fields exact, radii to rounding
+    own, r_own = _summary_of(err, np.moveaxis(pv[0:3], 0, -1))
+    for f in ("n_ok", "first_error", "k_first_error"):
+        assert np.array_equal(s[f], own[f]), f
+    has = own["n_ok"] > 0
+    assert np.array_equal(s["k_min"] >= 0, has) and np.array_equal(s["k_max"] >= 0, has)
+    assert np.isposinf(s["r_min"][~has]).all() and np.isneginf(s["r_max"][~has]).all()
+    rows = np.arange(b.n)[has]
+    for kf, rf in (("k_min", "r_min"), ("k_max", "r_max")):
+        assert (err[rows, s[kf][has]] == 0).all()
+        # the kernel's sqrt(fma chain) and numpy's differ by an ulp: the index may move only
+        # between evaluations whose radii tie to rounding
+        assert np.abs(r_own[rows, s[kf][has]] / own[rf][has] - 1.0).max() < 1e-14, kf
+        assert np.abs(s[rf][has] / own[rf][has] - 1.0).max() < 1e-14, rf
+    assert (s["k_min"] == own["k_min"]).mean() > 0.999 and (s["k_max"] == own["k_max"]).mean() > 0.999
+
+    # (2) against the oracle (the reference's results): codes exact, radii within the parity bar
+    eo, ro, _, _ = orc.propagate_grid(ta, tb, use_jd=use_jd, nthreads=8)
+    want, r_or = _summary_of(eo, ro)
+    for f in ("n_ok", "first_error", "k_first_error"):
+        assert np.array_equal(s[f], want[f]), f
+    bar = TOL_POS_KM + SENS_GAIN * np.where(eo == 0, sr, 0.0).max(1)
+    regular = has & (bar < 2 * TOL_POS_KM)
+    assert regular.sum() > 0.9 * has.sum()
+    assert (np.abs(s["r_min"][has] - want["r_min"][has]) <= bar[has]).all()
+    assert (np.abs(s["r_max"][has] - want["r_max"][has]) <= bar[has]).all()
+    # the time index the GPU picked is a minimiser / maximiser of the oracle's radii as well
+    assert (np.abs(r_or[rows, s["k_min"][has]] - want["r_min"][has]) <= 2 * bar[has]).all()
+    assert (np.abs(r_or[rows, s["k_max"][has]] - want["r_max"][has]) <= 2 * bar[has]).all()
+
+
+def test_fused_summary_device_output_and_chunk_boundaries():
+    """Device-resident result == host result, for grids that end on / straddle the 64-time warp
+    chunk and the 256-time tile."""
+    import torch
+    L1, L2 = _mixed_batch(700, seed=9)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    jd, fr = pb.synth_time_grid(1030)
+    for m in (63, 64, 65, 256, 257, 1030):
+        host = b.propagate_summary(jd[:m], fr[:m])
+        dev = torch.zeros(b.n * host.dtype.itemsize, dtype=torch.uint8, device="cuda")
+        b.propagate_summary_device(torch.as_tensor(jd[:m]).cuda(), torch.as_tensor(fr[:m]).cuda(), dev)
+        b.synchronize()
+        got = np.frombuffer(dev.cpu().numpy().tobytes(), dtype=host.dtype)
+        assert got.tobytes() == host.tobytes(), m
+        pv, err = b.propagate(jd[:m], fr[:m])
+        own, _ = _summary_of(err, np.moveaxis(pv[0:3], 0, -1))
+        for f in ("n_ok", "first_error", "k_first_error"):
+            assert np.array_equal(host[f], own[f]), (m, f)
+    assert b.last_launch_count() >= 2
 
 
 # ---- N4: classical orbital elements of the propagated states -----------------------------------
