@@ -28,6 +28,8 @@ __global__ void probe_kernel(int fn, const double *x, const double *y, double *o
         case 12: pb::sincos_small(a, s, c); r = c; break;
         case 13: r = pb::pow_2o3(a); break;
         case 14: r = pb::div_coarse(a, b); break;
+        case 15: pb::sincos_small<9>(a, s, c); r = s; break;
+        case 16: pb::sincos_small<9>(a, s, c); r = c; break;
         default: r = 0.0; break;
     }
     out[i] = r;

@@ -14,8 +14,11 @@
 //     from PF_AOBASE; sin/cos(inclo) come from PF_SINIO/PF_COSIO;
 //   * bstar*cc4 and bstar*cc5 are hoisted (the reference evaluates them left to right, so
 //     the hoisted products are the same doubles);
-//   * libm calls are replaced by the range-bounded routines of sgp4_math.cuh, divisions by
-//     reciprocal-multiply, and atan2 + sincos of the argument of latitude by a rotation.
+//   * libm calls are replaced by the routines of sgp4_math.cuh, divisions by reciprocal-
+//     multiply, atan2 + sincos of the argument of latitude by a rotation of the (unit) vector
+//     (sinu, cosu), sqrt(pl) by sqrt(am) sqrt(1 - el2), and sin/cos of angles that differ from
+//     an angle with known sin/cos by a small amount (drag correction of M, the solar / lunar
+//     equation of centre in dpper, the perturbed inclination) by short Taylor rotations.
 // The record fields the reference overwrites on every call (t, error, am..nm, and for deep
 // space aycof/xlcof/con41/x1mth2/x7thm1) are returned through `Sgp4Side` when asked for.
 #ifndef PERTURB_B200_SGP4_EVAL_CUH
@@ -68,15 +71,8 @@ struct ClassTraits<PB_CLS_RUNTIME> {
 // in-line fall-back must produce the same bits no matter how the compiler would contract
 // either copy.
 namespace res {
-// sin / cos of the phase constants of src/sgp4.cpp:1036-1043 (the doubles the reference uses)
-constexpr double s_fasx2 = 0.13093206501640100313, c_fasx2 = 0.99139134268488593686;  // 0.13130908
-constexpr double s_fasx4 = 0.25444411220371228015, c_fasx4 = -0.96708747989251968989; // 2.8843198
-constexpr double s_fasx6 = 0.36578942533149936234, c_fasx6 = 0.93069763957778009002;  // 0.37448087
-constexpr double s_g22 = -0.49213943048915524715, c_g22 = 0.87051638752972935101;     // 5.7686396
-constexpr double s_g32 = 0.81481440616389247062, c_g32 = 0.57972190187001152474;      // 0.95240898
-constexpr double s_g44 = 0.97350577801807993413, c_g44 = -0.22866241528815546759;     // 1.8014998
-constexpr double s_g52 = 0.86783740128127729936, c_g52 = 0.49684831179884195924;      // 1.0508330
-constexpr double s_g54 = -0.95489237761530004228, c_g54 = -0.29695209575316896683;    // 4.4108898
+// sin / cos of the phase constants of src/sgp4.cpp:1036-1043 live in the constant table
+// (kMc[MC_S_FASX2] ...): the doubles the reference uses, correctly rounded.
 
 // (sin, cos) of a + b from those of a and b
 __device__ __forceinline__ void add(double sa, double ca, double sb, double cb, double &s,
@@ -106,15 +102,15 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
                                                 double atime, double &xndt, double &xldot,
                                                 double &xnddt) {
     double sl, cl;
-    sincos_cw(wrap_pi2(xli), sl, cl);
+    sincos_cw(xli, sl, cl);
     if (irez != 2) {
         // theta1 = xli - fasx2, theta2 = 2 (xli - fasx4), theta3 = 3 (xli - fasx6)
         double s1, c1, s, c;
-        res::sub(sl, cl, res::s_fasx2, res::c_fasx2, s1, c1);
-        res::sub(sl, cl, res::s_fasx4, res::c_fasx4, s, c);
+        res::sub(sl, cl, kMc[MC_S_FASX2], kMc[MC_C_FASX2], s1, c1);
+        res::sub(sl, cl, kMc[MC_S_FASX4], kMc[MC_C_FASX4], s, c);
         const double s2 = __dmul_rn(__dadd_rn(s, s), c);
         const double c2 = __fma_rn(-__dadd_rn(s, s), s, 1.0);
-        res::sub(sl, cl, res::s_fasx6, res::c_fasx6, s, c);
+        res::sub(sl, cl, kMc[MC_S_FASX6], kMc[MC_C_FASX6], s, c);
         const double f = __fma_rn(-4.0 * s, s, 1.0);        // 1 - 4 s^2
         const double s3 = __dmul_rn(s, __dadd_rn(f, 2.0));  // s (3 - 4 s^2)
         const double c3 = __dmul_rn(c, f);                   // c (4 c^2 - 3) = c (1 - 4 s^2)
@@ -127,7 +123,7 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
     } else {
         const double xomi = __fma_rn(k(PF_ARGPDOT), atime, k(PF_ARGPO));
         double so, co;
-        sincos_cw(wrap_pi2(xomi), so, co);
+        sincos_cw(xomi, so, co);
         const double s2o = __dmul_rn(__dadd_rn(so, so), co), c2o = __fma_rn(-__dadd_rn(so, so), so, 1.0);
         const double s2l = __dmul_rn(__dadd_rn(sl, sl), cl), c2l = __fma_rn(-__dadd_rn(sl, sl), sl, 1.0);
         double sA, cA, sB, cB;
@@ -135,19 +131,19 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
         double ys = 0.0, yc = 0.0;   // same for the terms the reference doubles in xnddt (44, 54)
         // g22: (2 xomi + xli), (xli)
         res::add(s2o, c2o, sl, cl, sA, cA);
-        res::pair(k(PF_D2201), sA, cA, k(PF_D2211), sl, cl, res::s_g22, res::c_g22, xs, xc);
+        res::pair(k(PF_D2201), sA, cA, k(PF_D2211), sl, cl, kMc[MC_S_G22], kMc[MC_C_G22], xs, xc);
         // g32 and g52 share (xomi + xli), (xli - xomi)
         res::add(so, co, sl, cl, sA, cA);
         res::sub(sl, cl, so, co, sB, cB);
-        res::pair(k(PF_D3210), sA, cA, k(PF_D3222), sB, cB, res::s_g32, res::c_g32, xs, xc);
-        res::pair(k(PF_D5220), sA, cA, k(PF_D5232), sB, cB, res::s_g52, res::c_g52, xs, xc);
+        res::pair(k(PF_D3210), sA, cA, k(PF_D3222), sB, cB, kMc[MC_S_G32], kMc[MC_C_G32], xs, xc);
+        res::pair(k(PF_D5220), sA, cA, k(PF_D5232), sB, cB, kMc[MC_S_G52], kMc[MC_C_G52], xs, xc);
         // g44: (2 xomi + 2 xli), (2 xli)
         res::add(s2o, c2o, s2l, c2l, sA, cA);
-        res::pair(k(PF_D4410), sA, cA, k(PF_D4422), s2l, c2l, res::s_g44, res::c_g44, ys, yc);
+        res::pair(k(PF_D4410), sA, cA, k(PF_D4422), s2l, c2l, kMc[MC_S_G44], kMc[MC_C_G44], ys, yc);
         // g54: (xomi + 2 xli), (2 xli - xomi)
         res::add(so, co, s2l, c2l, sA, cA);
         res::sub(s2l, c2l, so, co, sB, cB);
-        res::pair(k(PF_D5421), sA, cA, k(PF_D5433), sB, cB, res::s_g54, res::c_g54, ys, yc);
+        res::pair(k(PF_D5421), sA, cA, k(PF_D5433), sB, cB, kMc[MC_S_G54], kMc[MC_C_G54], ys, yc);
         xndt = __dadd_rn(xs, ys);
         xldot = __dadd_rn(xni, k(PF_XFACT));
         xnddt = __dmul_rn(__fma_rn(2.0, yc, xc), xldot);
@@ -158,8 +154,8 @@ __device__ __forceinline__ void resonance_rates(const K &k, int irez, double xli
 __device__ __forceinline__ void resonance_advance(double xndt, double xldot, double xnddt,
                                                   double delt, double &xli, double &xni,
                                                   double &atime) {
-    xli = __fma_rn(xndt, 259200.0, __fma_rn(xldot, delt, xli));
-    xni = __fma_rn(xnddt, 259200.0, __fma_rn(xndt, delt, xni));
+    xli = __fma_rn(xndt, kMc[MC_STEP2], __fma_rn(xldot, delt, xli));
+    xni = __fma_rn(xnddt, kMc[MC_STEP2], __fma_rn(xndt, delt, xni));
     atime = __dadd_rn(atime, delt);
 }
 
@@ -238,7 +234,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         // (scripts/ubench/fp64_mix.cu), so a select-heavy "one polynomial for sin or cos"
         // costs more than it saves.
         double sinm, cosm;
-        sincos_cw(wrap_pi2(xmdf), sinm, cosm);
+        sincos_cw(xmdf, sinm, cosm);
         const double delmtemp = 1.0 + k(PF_ETA) * cosm;
         const double delm = k(PF_XMCOF) * (delmtemp * delmtemp * delmtemp - k(PF_DELMO));
         const double temp = delomg + delm;
@@ -248,7 +244,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double t4 = t3 * t;
         tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
         double sind, cosd;
-        sincos_small(temp, sind, cosd);
+        sincos_small<6>(temp, sind, cosd);
         const double sin_mm = sinm * cosd + cosm * sind;
         tempe = tempe + k(PF_BC5) * (sin_mm - k(PF_SINMAO));
         templ = templ + k(PF_T3COF) * t3 + t4 * (k(PF_T4COF) + t * k(PF_T5COF));
@@ -261,8 +257,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     // ---- dspace, src/sgp4.cpp:1018-1166 ----
     if (deep) {
-        constexpr double rptim = 4.37526908801129966e-3;
-        const double theta = fmod_2pi(k(PF_GSTO) + t * rptim);
+        const double theta = fmod_2pi(k(PF_GSTO) + t * kMc[MC_RPTIM]);  // rptim, :1045
         em = em + k(PF_DEDT) * t;
         inclm = inclm + k(PF_DIDT) * t;
         argpm = argpm + k(PF_DOMDT) * t;
@@ -341,8 +336,8 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double sqrt_am = am * rsqrt_am;
     nm = g.xke * (rsqrt_am * rsqrt_am * rsqrt_am);  // xke / pow(am, 1.5)
     em = em - tempe;
-    PB_FAIL_IF(em >= 1.0 || em < -0.001, 1);  // :1873
-    if (em < 1.0e-6) em = 1.0e-6;
+    PB_FAIL_IF(em >= 1.0 || em < -kMc[MC_1EM3], 1);  // :1873
+    if (em < kMc[MC_1EM6]) em = kMc[MC_1EM6];
     mm = mm + no * templ;
     double xlm = mm + argpm + nodem;
 
@@ -377,12 +372,15 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     double ep = em, xincp = inclm, argpp = argpm, nodep = nodem, mp = mm;
     double sinip, cosip, aycof, xlcof;
     if (deep) {
-        constexpr double zns = 1.19459e-5, zes = 0.01675, znl = 1.5835218e-4, zel = 0.05490;
-        double zm, zf, sinzf, coszf, f2, f3, s0, c0, sinzm, unused;
-        zm = k(PF_ZMOS) + zns * t;
-        sincos_cw(wrap_pi2(zm), sinzm, unused);  // cheaper in issue slots than a select-based sin
-        zf = zm + 2.0 * zes * sinzm;
-        sincos_cw(wrap_pi2(zf), sinzf, coszf);
+        // zns, zes, znl, zel of :246-249 (kMc[MC_ZNS], kMc[MC_2ZES] = 2 zes, ...)
+        // zf = zm + 2 zes sin(zm): sin/cos(zf) by rotating (sin zm, cos zm) through the small
+        // equation-of-centre angle, |2 zes sin zm| <= 0.0335 (Sun) / 0.1098 (Moon), with Taylor
+        // sums sized for those bounds (truncation < 5e-18 / 7e-18): no second range reduction.
+        double zm, sinzf, coszf, f2, f3, s0, c0, sinzm, coszm, sd, cd;
+        zm = k(PF_ZMOS) + kMc[MC_ZNS] * t;
+        sincos_cw(zm, sinzm, coszm);
+        sincos_taylor<3, 4>(kMc[MC_2ZES] * sinzm, sd, cd);
+        rotate(sinzm, coszm, sd, cd, sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
         const double ses = k(PF_SE2) * f2 + k(PF_SE3) * f3;
@@ -390,10 +388,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double sls = k(PF_SL2) * f2 + k(PF_SL3) * f3 + k(PF_SL4) * sinzf;
         const double sghs = k(PF_SGH2) * f2 + k(PF_SGH3) * f3 + k(PF_SGH4) * sinzf;
         const double shs = k(PF_SH2) * f2 + k(PF_SH3) * f3;
-        zm = k(PF_ZMOL) + znl * t;
-        sincos_cw(wrap_pi2(zm), sinzm, unused);
-        zf = zm + 2.0 * zel * sinzm;
-        sincos_cw(wrap_pi2(zf), sinzf, coszf);
+        zm = k(PF_ZMOL) + kMc[MC_ZNL] * t;
+        sincos_cw(zm, sinzm, coszm);
+        sincos_taylor<4, 5>(kMc[MC_2ZEL] * sinzm, sd, cd);
+        rotate(sinzm, coszm, sd, cd, sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
         const double sel = k(PF_EE2) * f2 + k(PF_E3) * f3;
@@ -409,8 +407,11 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         double ph = shs + shll;
         xincp = xincp + pinc;
         ep = ep + pe;
-        sincos_cw(wrap_pi2(xincp), s0, c0);
-        if (xincp >= 0.2) {  // :317
+        // xincp = inclo + (didt t + pinc): rotate the per-satellite (sin, cos)(inclo) through
+        // the small secular + periodic change (1e-3 rad over a week; general routine beyond 2^-6)
+        sincos_small<6>(xincp - k(PF_INCLO), sd, cd);
+        rotate(k(PF_SINIO), k(PF_COSIO), sd, cd, s0, c0);
+        if (xincp >= kMc[MC_0P2]) {  // :317
             ph = div_fast(ph, s0);
             pgh = pgh - c0 * ph;
             argpp = argpp + pgh;
@@ -418,7 +419,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             mp = mp + pl;
         } else {  // Lyddane modification, :325-364
             double sinop, cosop;
-            sincos_cw(wrap_pi2(nodep), sinop, cosop);
+            sincos_cw(nodep, sinop, cosop);
             double alfdp = s0 * sinop;
             double betdp = s0 * cosop;
             const double dalf = ph * cosop + pinc * c0 * sinop;
@@ -426,18 +427,18 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             alfdp = alfdp + dalf;
             betdp = betdp + dbet;
             nodep = fmod_2pi(nodep);
-            if (nodep < 0.0 && opsmode_a) nodep = nodep + kTwoPi;
+            if (nodep < 0.0 && opsmode_a) nodep = nodep + kMc[MC_TWOPI];
             double xls = mp + argpp + c0 * nodep;
             const double dls = pl + pgh - pinc * nodep * s0;
             xls = xls + dls;
             const double xnoh = nodep;
             nodep = atan2(alfdp, betdp);
-            if (nodep < 0.0 && opsmode_a) nodep = nodep + kTwoPi;
-            if (fabs(xnoh - nodep) > kPi) {
+            if (nodep < 0.0 && opsmode_a) nodep = nodep + kMc[MC_TWOPI];
+            if (fabs(xnoh - nodep) > kMc[MC_PI]) {
                 if (nodep < xnoh) {
-                    nodep = nodep + kTwoPi;
+                    nodep = nodep + kMc[MC_TWOPI];
                 } else {
-                    nodep = nodep - kTwoPi;
+                    nodep = nodep - kMc[MC_TWOPI];
                 }
             }
             mp = mp + pl;
@@ -449,13 +450,13 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         cosip = c0;
         if (xincp < 0.0) {  // :1932
             xincp = -xincp;
-            nodep = nodep + kPi;
-            argpp = argpp - kPi;
+            nodep = nodep + kMc[MC_PI];
+            argpp = argpp - kMc[MC_PI];
             sinip = -s0;
         }
         PB_FAIL_IF(ep < 0.0 || ep > 1.0, 3);  // :1938
         aycof = -0.5 * g.j3oj2 * sinip;
-        if (fabs(cosip + 1.0) > 1.5e-12) {
+        if (fabs(cosip + 1.0) > kMc[MC_1P5EM12]) {
             xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), 1.0 + cosip);
         } else {
             xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / 1.5e-12;
@@ -474,7 +475,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     // ---- long-period periodics and Kepler's equation, src/sgp4.cpp:1959-1983 ----
     double sinargp, cosargp;
-    sincos_cw(deep ? wrap_pi2(argpp) : argpp, sinargp, cosargp);
+    sincos_cw(argpp, sinargp, cosargp);
     const double axnl = ep * cosargp;
     double temp = rcp_fast(am * (1.0 - ep * ep));
     const double aynl = ep * sinargp + temp * aycof;
@@ -505,12 +506,12 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         sincos_cw(eo1, sn, cs);
         double tem5 = 1.0 - cs * axnl - sn * aynl;
         tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
-        if (fabs(tem5) >= 0.95) tem5 = tem5 > 0.0 ? 0.95 : -0.95;
+        if (fabs(tem5) >= kMc[MC_0P95]) tem5 = tem5 > 0.0 ? kMc[MC_0P95] : -kMc[MC_0P95];
         const double mag = fabs(tem5);
         if (active) {
             sineo1 = sn;
             coseo1 = cs;
-            if (!(mag >= 1.0e-12)) {
+            if (!(mag >= kMc[MC_1EM12])) {
                 active = false;  // the reference stops here, state as evaluated
             } else if (mag < 5.9604644775390625e-8 && ktr < 10) {
                 dfin = tem5;     // the reference would make one confirming pass at E + d
@@ -540,8 +541,8 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double rl = am * (1.0 - ecose);
     const double inv_rl = rcp_fast(rl);
     const double rdotl = sqrt_am * esine * inv_rl;
-    const double rvdotl = sqrt_fast(pl) * inv_rl;
     const double betal = sqrt_fast(1.0 - el2);
+    const double rvdotl = (sqrt_am * betal) * inv_rl;  // sqrt(pl) = sqrt(am) sqrt(1 - el2)
     temp = esine * rcp_fast(1.0 + betal);
     const double aorl = am * inv_rl;
     const double sinu = aorl * (sineo1 - aynl - axnl * temp);
@@ -583,21 +584,21 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     // ---- orientation vectors, position and velocity, src/sgp4.cpp:2031-2052 ----
     double sinsu, cossu, snod, cnod, sini, cosi;
     {
-        const double h2 = sinu * sinu + cosu * cosu;
-        const double inv_h = rsqrt_fast(h2);
-        const bool degenerate = !(h2 > 0.0);  // atan2(0, 0) == 0; selects, not branches
-        const double su_s = degenerate ? 0.0 : sinu * inv_h;
-        const double su_c = degenerate ? 1.0 : cosu * inv_h;
+        // (sinu, cosu) is a unit vector by construction: with r = a (1 - e cos E) and
+        // beta = sqrt(1 - e^2), sinu^2 + cosu^2 == 1 is an algebraic identity in E (any E,
+        // converged or not), so atan2 followed by sin/cos would only remove rounding noise of
+        // a few 1e-16 (times a/r near the perigee of a very eccentric orbit) from the norm.
+        const double su_s = sinu, su_c = cosu;
         double sd, cd;
-        sincos_small(dsu, sd, cd);
+        sincos_small<9>(dsu, sd, cd);
         sinsu = su_s * cd - su_c * sd;
         cossu = su_c * cd + su_s * sd;
     }
-    sincos_cw(deep ? wrap_pi2(xnode) : xnode, snod, cnod);
+    sincos_cw(xnode, snod, cnod);
     {
         // xinc = xincp + dxi with dxi ~ 1e-3 and sin/cos(xincp) already at hand
         double sdx, cdx;
-        sincos_small(dxi, sdx, cdx);
+        sincos_small<9>(dxi, sdx, cdx);
         sini = sinip * cdx + cosip * sdx;
         cosi = cosip * cdx - sinip * sdx;
     }
@@ -610,12 +611,14 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double vy = xmy * cossu - snod * sinsu;
     const double vz = sini * cossu;
 
-    out[0] = (mrt * ux) * g.radiusearthkm;
-    out[1] = (mrt * uy) * g.radiusearthkm;
-    out[2] = (mrt * uz) * g.radiusearthkm;
-    out[3] = (mvt * ux + rvdot * vx) * g.vkmpersec;
-    out[4] = (mvt * uy + rvdot * vy) * g.vkmpersec;
-    out[5] = (mvt * uz + rvdot * vz) * g.vkmpersec;
+    const double mr = mrt * g.radiusearthkm;
+    const double mv = mvt * g.vkmpersec, rv = rvdot * g.vkmpersec;
+    out[0] = mr * ux;
+    out[1] = mr * uy;
+    out[2] = mr * uz;
+    out[3] = mv * ux + rv * vx;
+    out[4] = mv * uy + rv * vy;
+    out[5] = mv * uz + rv * vz;
 
     PB_FAIL_IF(mrt < 1.0, 6);  // :2056
 #undef PB_FAIL_IF

@@ -42,9 +42,9 @@ enum {
 // [0, PF_FULL_END) near-Earth full drag, [0, PF_COMMON_END) + [PF_FULL_END, PF_COUNT) deep.
 #define PB_PROP_FIELDS(X)                                                                    \
     X(JD0) X(JDF0) X(MO) X(MDOT) X(ARGPO) X(ARGPDOT) X(NODEO) X(NODEDOT) X(NODECF) X(CC1)     \
-    X(BC4) X(T2COF) X(NO) X(ECCO) X(INCLO) X(AOBASE)                                         \
+    X(BC4) X(T2COF) X(NO) X(ECCO) X(INCLO) X(AOBASE) X(SINIO) X(COSIO)                       \
     /* near-Earth only */                                                                    \
-    X(SINIO) X(COSIO) X(AYCOF) X(XLCOF) X(CON41) X(X1MTH2) X(X7THM1)                          \
+    X(AYCOF) X(XLCOF) X(CON41) X(X1MTH2) X(X7THM1)                                           \
     /* near-Earth full drag only */                                                          \
     X(OMGCOF) X(ETA) X(XMCOF) X(DELMO) X(D2) X(D3) X(D4) X(BC5) X(SINMAO) X(T3COF) X(T4COF)   \
     X(T5COF)                                                                                 \
@@ -62,7 +62,7 @@ enum {
     PB_PROP_FIELDS(X)
 #undef X
     PF_COUNT,
-    PF_COMMON_END = PF_AOBASE + 1,
+    PF_COMMON_END = PF_COSIO + 1,
     PF_NEAR_END = PF_X7THM1 + 1,
     PF_FULL_END = PF_T5COF + 1,
     PF_DEEP_NR_END = PF_ZMOS + 1,

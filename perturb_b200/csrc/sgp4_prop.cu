@@ -20,14 +20,18 @@ namespace pb {
 
 namespace {
 
-// Resident CTAs per SM the register allocation is capped for (measured on B200, sweep in
-// profiles/r1_sweeps.md): near-Earth bodies fit 80 registers with a handful of spills and
-// gain from 24 warps/SM; the deep-space bodies are larger and do best at 4 CTAs (128 regs).
+// Resident CTAs per SM the register allocation is capped for (measured on B200, sweeps in
+// profiles/): the near-Earth bodies need 64-70 registers and do best at 7 CTAs (28 warps/SM;
+// 8 is 1.5 % slower), the deep-space bodies at 5 (<= 102 registers; the 12 h-resonant one
+// spills 20 bytes there and is still faster than at 4).
 #ifndef PB_MIN_BLOCKS_NEAR
-#define PB_MIN_BLOCKS_NEAR 5
+#define PB_MIN_BLOCKS_NEAR 7
 #endif
 #ifndef PB_MIN_BLOCKS_DEEP
-#define PB_MIN_BLOCKS_DEEP 4
+#define PB_MIN_BLOCKS_DEEP 5
+#endif
+#ifndef PB_MIN_BLOCKS_R2
+#define PB_MIN_BLOCKS_R2 5
 #endif
 #ifndef PB_WARPS
 #define PB_WARPS 4
@@ -58,7 +62,7 @@ template <int CLS>
 struct SmemConsts {  // constants of satellite `s` of the staged tile: broadcast LDS.64
     const double *base;
     __device__ __forceinline__ double operator()(int f) const {
-        return base[TileFields<CLS>::row(f) * PB_TILE_SATS];
+        return base[TileFields<CLS>::row(f)];
     }
 };
 
@@ -229,11 +233,14 @@ __device__ __forceinline__ void merge_summary(LaneSummary &a, const LaneSummary 
 }
 
 template <int CLS, int MODE>
-__global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR : PB_MIN_BLOCKS_DEEP)
+__global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR
+                                           : (CLS == PB_CLS_DEEP_R2) ? PB_MIN_BLOCKS_R2
+                                                                     : PB_MIN_BLOCKS_DEEP)
 sgp4_prop_kernel(const PropParams p) {
     constexpr bool WANT_ELEMENTS = (MODE == kModeElements);
     using TF = TileFields<CLS>;
-    __shared__ double s_pf[TF::kRows * PB_TILE_SATS];
+    constexpr int kRowsPad = (TF::kRows + 1) & ~1;  // even: every satellite's block 16 B aligned
+    __shared__ __align__(16) double s_pf[kRowsPad * PB_TILE_SATS];
     __shared__ double s_ta[kTimeTile];
     __shared__ double s_tb[kTimeTile];
     __shared__ int s_perm[PB_TILE_SATS];
@@ -250,7 +257,7 @@ sgp4_prop_kernel(const PropParams p) {
     // ---- stage constants (coalesced 256 B rows) and this CTA's slice of the time grid ----
     for (int r = warp; r < TF::kRows; r += kWarps) {
         const int f = r < TF::kEndA ? r : r - TF::kEndA + TF::kBeginB;
-        s_pf[r * PB_TILE_SATS + lane] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + lane];
+        s_pf[lane * kRowsPad + r] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + lane];
     }
     if (threadIdx.x < PB_TILE_SATS) s_perm[threadIdx.x] = p.perm[sat0 + threadIdx.x];
     if (kResonant && threadIdx.x < PB_TILE_SATS) {
@@ -274,6 +281,9 @@ sgp4_prop_kernel(const PropParams p) {
     // bytes per plane (full sectors) issued right after the evaluation.
     const int i0 = warp * (32 * kTpl) + lane;
     if (k_base + warp * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
+    // (Skipping the second group of 32 times when only it lies beyond the grid -- 1440 = 22 x 64
+    // + 32 -- was measured: a data-dependent trip count makes ptxas treat the body as divergent,
+    // +1.4 % instructions per evaluation for 2.2 % fewer evaluations, and slower overall.)
     double ta[kTpl], tb[kTpl];
 #pragma unroll
     for (int j = 0; j < kTpl; ++j) {
@@ -287,7 +297,7 @@ sgp4_prop_kernel(const PropParams p) {
     for (int s = 0; s < PB_TILE_SATS; ++s) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
-        const SmemConsts<CLS> k = {s_pf + s};
+        const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
         ResNodes nodes = {nullptr, 0, 0, 0};
         if (kResonant) {
             nodes.base = p.res_nodes + (sat0 + s - p.res_first_slot);
@@ -312,6 +322,9 @@ sgp4_prop_kernel(const PropParams p) {
                 k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
                 kResonant ? &nodes : nullptr);
             const int kt = k_base + i0 + 32 * j;
+            // every lane of the warp is here (uniform control flow): one vote decides whether
+            // the stores need the NaN selects at all
+            const bool all_written = __all_sync(0xffffffffu, (cd == 0) || (cd == 6));
             if (WANT_ELEMENTS && kt < p.m) {
                 // what sgp4() leaves in satrec (src/sgp4.cpp:1895-1901); not reached for codes 1, 2
                 const bool stored = side.stage >= 1;
@@ -339,9 +352,12 @@ sgp4_prop_kernel(const PropParams p) {
             } else if (kt < p.m) {
                 // codes 1-4: the reference leaves the caller's state untouched -> NaN
                 const bool written = (cd == 0) || (cd == 6);
+                if (all_written) {
 #pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    row[c * p.plane_stride + kt] = written ? r[c] : nan;
+                    for (int c = 0; c < 6; ++c) row[c * p.plane_stride + kt] = r[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) row[c * p.plane_stride + kt] = written ? r[c] : nan;
                 }
                 erow[kt] = cd;
             }

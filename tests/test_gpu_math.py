@@ -44,6 +44,12 @@ def test_sincos_small_angle_path():
     d = np.concatenate([rng.uniform(-0.0156, 0.0156, N), rng.uniform(-3.0, 3.0, 5000), [0.0]])
     assert np.abs(probe(11, d) - np.sin(d)).max() < 2.3e-16
     assert np.abs(probe(12, d) - np.cos(d)).max() < 2.3e-16
+    # the two-coefficient series (|d| < 2^-9: short-period corrections), same fall-back
+    d9 = np.concatenate([rng.uniform(-0.00196, 0.00196, N), rng.uniform(-3.0, 3.0, 5000), [0.0]])
+    assert np.abs(probe(15, d9) - np.sin(d9)).max() < 2.3e-16
+    assert np.abs(probe(16, d9) - np.cos(d9)).max() < 2.3e-16
+    tiny = rng.uniform(-0.0156, 0.0156, N)
+    assert ulps(probe(11, tiny), np.sin(tiny)).max() <= 1.0
 
 
 def test_division_reciprocal_sqrt():
