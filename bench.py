@@ -46,8 +46,8 @@ WORKLOADS = {
     "c4s": (4, 50000, 2016),
     "c5s": (5, 125000, 2000),
     # small cuts for ncu --set full (ncu saves and restores every output byte per replay pass)
-    "c3p": (3, 20000, 1024),
-    "c4p": (4, 10000, 1024),
+    "c3p": (3, 100000, 512),
+    "c4p": (4, 50000, 1024),
 }
 WORKLOAD_TEXT = {
     "c2": "30k near-Earth synthetic LEO catalogue x 1440 one-minute steps per GPU",
@@ -57,8 +57,8 @@ WORKLOAD_TEXT = {
     "c3s": "100k mixed catalogue x 2000 steps per GPU (time-chunk of c3)",
     "c4s": "50k GEO + Molniya catalogue x 2016 steps per GPU (time-chunk of c4)",
     "c5s": "125k mega-constellation satellites x 2000 steps per GPU (time-chunk of c5)",
-    "c3p": "20k mixed catalogue x 1024 steps (profiling cut of c3)",
-    "c4p": "10k GEO + Molniya catalogue x 1024 steps (profiling cut of c4)",
+    "c3p": "100k mixed catalogue x 512 steps (profiling cut of c3)",
+    "c4p": "50k GEO + Molniya catalogue x 1024 steps (profiling cut of c4)",
 }
 E2E_MAX_TIMES = 2000  # host-buffer arm: at most this many times per step (bounds pinned memory)
 

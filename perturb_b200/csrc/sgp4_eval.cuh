@@ -327,7 +327,14 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
 
     double aobase;
     if (deep && irez != 0) {
-        aobase = pow_2o3(div_fast(g.xke, nm));
+        // pow(xke / nm, 2/3) with nm = no (1 + x): AOBASE (1 + x)^(-2/3); the resonance moves
+        // the mean motion by 1e-5 .. 1e-3 of itself, so a six-term binomial series replaces
+        // cbrt + division; anything larger takes the general route.
+        const double x = (nm - no) * rcp_fast(no);
+        aobase = k(PF_AOBASE) * pow_m2o3_1p(x);
+        if (!(fabs(x) < 0.00390625)) {
+            aobase = pow_2o3(div_fast(g.xke, nm));
+        }
     } else {
         aobase = k(PF_AOBASE);  // nm == no_unkozai: pow(xke/no, 2/3) is a constant
     }
@@ -346,9 +353,17 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         // against atan2 output (:352): the representative matters, keep C fmod semantics. The
         // same holds when the mean elements are handed back to the record (Om, om, mm).
         nodem = fmod_2pi(nodem);
-        argpm = fmod_2pi(argpm);
-        xlm = fmod_2pi(xlm);
-        mm = fmod_2pi(xlm - argpm - nodem);
+        if (WANT_SIDE) {
+            argpm = fmod_2pi(argpm);
+            xlm = fmod_2pi(xlm);
+            mm = fmod_2pi(xlm - argpm - nodem);
+        } else {
+            // only nodem's representative reaches a result (dpper's Lyddane branch, above);
+            // argpm, xlm and mm feed sums that are reduced again and sin/cos
+            argpm = wrap_pi(argpm);
+            xlm = wrap_pi(xlm);
+            mm = wrap_pi(xlm - argpm - nodem);
+        }
     } else {
         // near-Earth: these angles only enter sin/cos and sums that are reduced again
         nodem = wrap_pi(nodem);
@@ -418,29 +433,24 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             nodep = nodep + ph;
             mp = mp + pl;
         } else {  // Lyddane modification, :325-364
-            double sinop, cosop;
-            sincos_cw(nodep, sinop, cosop);
-            double alfdp = s0 * sinop;
-            double betdp = s0 * cosop;
-            const double dalf = ph * cosop + pinc * c0 * sinop;
-            const double dbet = -ph * sinop + pinc * c0 * cosop;
-            alfdp = alfdp + dalf;
-            betdp = betdp + dbet;
+            // The reference forms alfdp = A sin(node) + ph cos(node), betdp = A cos(node) -
+            // ph sin(node) with A = sin(i) + pinc cos(i) and takes atan2(alfdp, betdp), then
+            // moves the result by +-2pi onto the branch within pi of the old node: that IS
+            // node + atan2(ph, A). No sin/cos of the node, and for |ph| < A / 4 (every
+            // satellite but those within ~1e-3 rad of the equator) a 1-ulp polynomial arctangent
+            // of the small ratio instead of a general atan2.
+            const double A = s0 + pinc * c0;
+            const double tq = div_fast(ph, A);
+            double dnode = atan_small(tq);
+            if (!(fabs(ph) < 0.25 * A)) {  // per lane: this branch is not warp-uniform anyway
+                dnode = atan2(ph, A);
+            }
             nodep = fmod_2pi(nodep);
             if (nodep < 0.0 && opsmode_a) nodep = nodep + kMc[MC_TWOPI];
             double xls = mp + argpp + c0 * nodep;
             const double dls = pl + pgh - pinc * nodep * s0;
             xls = xls + dls;
-            const double xnoh = nodep;
-            nodep = atan2(alfdp, betdp);
-            if (nodep < 0.0 && opsmode_a) nodep = nodep + kMc[MC_TWOPI];
-            if (fabs(xnoh - nodep) > kMc[MC_PI]) {
-                if (nodep < xnoh) {
-                    nodep = nodep + kMc[MC_TWOPI];
-                } else {
-                    nodep = nodep - kMc[MC_TWOPI];
-                }
-            }
+            nodep = nodep + dnode;
             mp = mp + pl;
             argpp = xls - mp - c0 * nodep;
         }
@@ -486,42 +496,37 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     // stop after one smaller than 1e-12; the sin/cos it keeps are those of the iterate BEFORE
     // that last correction, which is never applied to them).
     //
-    // Two observations make this cheaper without leaving the reference's fixed point:
+    // Three observations make this cheaper without leaving the reference's fixed point:
     //  * Newton converges quadratically, so once a correction d is below 6e-8 the NEXT one
     //    would be < e d^2 / (2 (1 - e)) < 1e-12: the reference's next pass only re-evaluates
     //    sin/cos at E + d and stops. That pass is replaced by rotating (sin E, cos E) by d
     //    (second-order series, error < 1e-22) after the loop.
-    //  * a lane that has finished keeps its state, so a result never depends on how many
-    //    iterations the other lanes of the warp (other times of the same satellite) need.
-    double eo1 = u, sineo1 = 1.0, coseo1 = 1.0, dfin = 0.0;
-    bool active = true;
+    //  * a lane that has finished only stops moving its iterate: the later passes the rest of
+    //    the warp needs recompute the very same sin/cos and correction from the frozen
+    //    iterate (same instructions, same inputs), so nothing has to be saved or selected per
+    //    pass, and a result never depends on how many iterations the other lanes of the warp
+    //    (other times of the same satellite) need.
+    //  * the clamp is two selects; a NaN correction stays NaN and stops the lane, as in the
+    //    reference.
+    double eo1 = u, sineo1, coseo1, tem5, mag;
+    bool done = false;
+    int ktr = 1;
 #pragma unroll 1
-    for (int ktr = 1; ktr <= 10; ++ktr) {
-        if (UNIFORM) {
-            if (!__any_sync(0xffffffffu, active)) break;
-        } else if (!active) {
-            break;
-        }
-        double sn, cs;
-        sincos_cw(eo1, sn, cs);
-        double tem5 = 1.0 - cs * axnl - sn * aynl;
-        tem5 = div_coarse(u - aynl * cs + axnl * sn - eo1, tem5);
-        if (fabs(tem5) >= kMc[MC_0P95]) tem5 = tem5 > 0.0 ? kMc[MC_0P95] : -kMc[MC_0P95];
-        const double mag = fabs(tem5);
-        if (active) {
-            sineo1 = sn;
-            coseo1 = cs;
-            if (!(mag >= kMc[MC_1EM12])) {
-                active = false;  // the reference stops here, state as evaluated
-            } else if (mag < 5.9604644775390625e-8 && ktr < 10) {
-                dfin = tem5;     // the reference would make one confirming pass at E + d
-                active = false;
-            } else {
-                eo1 = eo1 + tem5;
-            }
-        }
-    }
-    {   // sin/cos at E + dfin (identity when dfin == 0)
+    do {
+        sincos_cw(eo1, sineo1, coseo1);
+        tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
+        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
+        tem5 = (tem5 > kMc[MC_0P95]) ? kMc[MC_0P95] : tem5;
+        tem5 = (tem5 < -kMc[MC_0P95]) ? -kMc[MC_0P95] : tem5;
+        mag = fabs(tem5);
+        // stop as evaluated (< 1e-12), or stop with one confirming rotation owed (< 6e-8)
+        const bool stop = !(mag >= kMc[MC_1EM12]) || (mag < 5.9604644775390625e-8 && ktr < 10);
+        done = done || stop;
+        if (!done) eo1 = eo1 + tem5;
+        ++ktr;
+    } while (ktr <= 10 && !(UNIFORM ? __all_sync(0xffffffffu, done) : done));
+    {   // sin/cos at E + d for the lanes that owe the confirming pass (identity otherwise)
+        const double dfin = (done && mag >= kMc[MC_1EM12]) ? tem5 : 0.0;
         const double h = dfin * dfin;
         const double sd = __fma_rn(-0.16666666666666666 * h, dfin, dfin);
         const double cd = __fma_rn(-0.5, h, 1.0);

@@ -58,6 +58,10 @@ enum {
     // sin / cos of the resonance phase constants, src/sgp4.cpp:1036-1043
     MC_S_FASX2, MC_C_FASX2, MC_S_FASX4, MC_C_FASX4, MC_S_FASX6, MC_C_FASX6, MC_S_G22, MC_C_G22,
     MC_S_G32, MC_C_G32, MC_S_G44, MC_C_G44, MC_S_G52, MC_C_G52, MC_S_G54, MC_C_G54,
+    // atan(t) = t + t^3 P(t^2) on |t| <= 0.25 (scripts/fit_atan.py 0.2501 8: 1 ulp)
+    MC_A0, MC_A1, MC_A2, MC_A3, MC_A4, MC_A5, MC_A6, MC_A7,
+    // (1 + x)^(-2/3) = 1 + x (B1 + x (B2 + ...)): binomial coefficients -2/3, 5/9, -40/81, ...
+    MC_B1, MC_B2, MC_B3, MC_B4, MC_B5, MC_B6,
     MC_COUNT
 };
 
@@ -88,6 +92,11 @@ static __constant__ double kMc[MC_COUNT] = {
     0.97350577801807993413, -0.22866241528815546759,  // g44 = 1.8014998
     0.86783740128127729936, 0.49684831179884195924,   // g52 = 1.0508330
     -0.95489237761530004228, -0.29695209575316896683, // g54 = 4.4108898
+    -3.33333333333333037274e-01, 1.99999999999382532812e-01, -1.42857142649373713983e-01,
+    1.11111084421623651508e-01, -9.09074023080557735987e-02, 7.68647824954676456288e-02,
+    -6.55414157038025635416e-02, 4.72544858625266947505e-02,
+    -6.66666666666666629659e-01, 5.55555555555555580227e-01, -4.93827160493827133081e-01,
+    4.52674897119341557161e-01, -4.22496570644718794085e-01, 3.99024538942234441308e-01,
 };
 
 // ---- reciprocal, division, square root ---------------------------------------------------
@@ -303,6 +312,24 @@ __device__ __forceinline__ void sincos_small(double d, double &s, double &c) {
     if (!(fabs(d) < (LEVEL <= 6 ? 0.015625 : 0.001953125))) {
         sincos_cw(d, s, c);
     }
+}
+
+// atan(t) for |t| <= 0.25, 1 ulp (no reduction, no quadrant logic): the angle by which the
+// Lyddane branch of dpper moves the node.
+__device__ __forceinline__ double atan_small(double t) {
+    const double z = __dmul_rn(t, t);
+    double p = kMc[MC_A7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i) p = __fma_rn(p, z, kMc[MC_A0 + i]);
+    return __fma_rn(__dmul_rn(t, z), p, t);
+}
+
+// (1 + x)^(-2/3) for |x| < 2^-8: binomial series through x^6 (next term 0.38 x^7 < 6e-18).
+__device__ __forceinline__ double pow_m2o3_1p(double x) {
+    double p = kMc[MC_B6];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) p = __fma_rn(p, x, kMc[MC_B1 + i]);
+    return __fma_rn(p, x, kMc[MC_ONE]);
 }
 
 // pow(x, 2/3) for x > 0 (the reference passes x2o3 = 2.0/3.0, src/sgp4.cpp:1795, 1867)
