@@ -358,16 +358,17 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             xlm = fmod_2pi(xlm);
             mm = fmod_2pi(xlm - argpm - nodem);
         } else {
-            // only nodem's representative reaches a result (dpper's Lyddane branch, above);
-            // argpm, xlm and mm feed sums that are reduced again and sin/cos
-            argpm = wrap_pi(argpm);
+            // only nodem's representative reaches a result (dpper's Lyddane branch, above).
+            // argpm stays unreduced: it grows by ~0.5 rad a week, enters sums that are reduced
+            // again (the 2 pi multiples drop out exactly in wrap_pi) and sin/cos, which take
+            // any angle.
             xlm = wrap_pi(xlm);
             mm = wrap_pi(xlm - argpm - nodem);
         }
     } else {
-        // near-Earth: these angles only enter sin/cos and sums that are reduced again
-        nodem = wrap_pi(nodem);
-        argpm = wrap_pi(argpm);
+        // near-Earth: nodem (~0.1 rad a week) and argpm (~0.5 rad a week) likewise stay
+        // unreduced; the fast angle, the mean anomaly, is reduced exactly where the reference
+        // reduces it (:1884-1887)
         xlm = wrap_pi(xlm);
         mm = wrap_pi(xlm - argpm - nodem);
     }
