@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 F_ALG = {0: 1170.0, 1: 1090.0, 2: 1502.0, 3: 1586.0, 4: 2097.0}
 BYTES_PER_EVAL = 52.0  # 48 B r,v + 4 B Sgp4Error written; reads amortise to < 1 B
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+N_SM = 148
 
 WORKLOADS = {
     # name: (synthetic config, satellites per GPU, times) -- BASELINE.json configs[1..4];
@@ -378,9 +379,19 @@ def run_gpu(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
+    pipe = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
-            args.workload)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = prof.get(args.workload)
+        # FP64 instructions per evaluation of each class kernel, counted by ncu (profiles/):
+        # the share of the FP64 pipe's issue cycles (2 warp instructions per clock per SM) the
+        # step keeps busy -- the quantity that bounds this kernel, next to the flops-v0 figure
+        ipe = prof.get("fp64_instr_per_eval")
+        if ipe and clocks.get("sm_mhz"):
+            instr = float(sum(ipe[c] * cls[c] for c in range(5))) * m / 32.0
+            cap = launch_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * N_SM * 2.0
+            pipe = {"fp64_warp_instr_per_step": instr, "frac_of_fp64_issue_cycles": instr / cap,
+                    "fp64_instr_per_eval": ipe, "source": prof.get("_fp64_instr_source")}
     except Exception:
         pass
     cpu = cpu_arm(args.workload, 2, 1) if world == 1 or rank == 0 else None
@@ -421,6 +432,10 @@ def run_gpu(args):
             "flops_per_eval": falg,
             "kernel": "sgp4_prop_kernel (all class launches of one step)",
             "launch_ms": launch_ms,
+            "note": "flops-v0 charges every sin/cos/div/sqrt at its libdevice fast-path cost "
+                    "(SURVEY.md 8d); the kernel needs fewer FP64 operations for the same "
+                    "evaluation, so frac can exceed 1 -- fp64_pipe is the executed-work view",
+            "fp64_pipe": pipe,
         },
         "roofline_hbm": {
             "bound": "hbm",
