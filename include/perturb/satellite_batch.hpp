@@ -117,52 +117,41 @@ public:
     }
 
     /// Batched `Satellite::propagate(jd, sv)` for every satellite and every time.
-    /// `svs` and `errs` are satellite-major [size() * m]; a StateVector is left untouched
-    /// for error codes 1-4, exactly like the reference (sgp4.cpp:1865,1878,1943,1995).
-    /// For throughput-critical callers use propagate_soa(), which avoids this transposition.
+    /// `svs` and `errs` are satellite-major [size() * m]. The device writes the 64-byte
+    /// `StateVector` records themselves (perturb_gpu_propagate_states), which are copied
+    /// straight into `svs`; `sv.epoch` is always set and position / velocity are left untouched
+    /// for error codes 1-4, exactly like the reference (sgp4.cpp:1865,1878,1943,1995) -- the
+    /// few rows that contain such an evaluation are found beforehand with the fused summary
+    /// pass, saved, and put back afterwards.
     int propagate(const JulianDate *times, std::size_t m, StateVector *svs, Sgp4Error *errs) {
         std::vector<double> jd(m), frac(m);
         for (std::size_t k = 0; k < m; ++k) {
             jd[k] = times[k].jd;
             frac[k] = times[k].jd_frac;
         }
-        std::vector<double> posvel(6 * n_ * m);
-        std::vector<std::int32_t> codes(n_ * m);
-        const int st = propagate_soa(
-            jd.data(), frac.data(), m, posvel.data(), codes.data(), m, n_ * m, nullptr
-        );
-        if (st != PERTURB_GPU_OK) {
-            return st;
-        }
-        scatter(posvel, codes, m, svs, errs);
-        for (std::size_t i = 0; i < n_; ++i) {
-            for (std::size_t k = 0; k < m; ++k) {
-                svs[i * m + k].epoch = times[k];  // perturb.cpp:240
-            }
-        }
-        return st;
+        return propagate_records(jd.data(), frac.data(), m, svs, errs);
     }
 
-    /// Batched `Satellite::propagate_from_epoch(mins, sv)` (perturb.cpp:228-234).
+    /// Batched `Satellite::propagate_from_epoch(mins, sv)` (perturb.cpp:228-234);
+    /// `sv.epoch = epoch(i) + mins / 1440` as the reference sets it.
     int propagate_from_epoch(
         const double *mins, std::size_t m, StateVector *svs, Sgp4Error *errs
     ) {
-        std::vector<double> posvel(6 * n_ * m);
-        std::vector<std::int32_t> codes(n_ * m);
-        status_ = perturb_gpu_propagate_from_epoch(
-            handle_, mins, m, posvel.data(), codes.data(), m, n_ * m, nullptr
+        return propagate_records(mins, nullptr, m, svs, errs);
+    }
+
+    /// The same without the save / restore: position and velocity of evaluations with error
+    /// codes 1-4 are quiet NaN (the C ABI's convention). `svs` may be host or device memory.
+    int propagate_states(
+        const double *jd, const double *jd_frac, std::size_t m, StateVector *svs,
+        Sgp4Error *errs, std::size_t row_stride, void *stream
+    ) {
+        status_ = perturb_gpu_propagate_states(
+            handle_, jd, jd_frac, m, reinterpret_cast<perturb_gpu_state *>(svs),
+            reinterpret_cast<std::int32_t *>(errs), row_stride, stream
         );
-        if (status_ == PERTURB_GPU_OK) {
+        if (status_ == PERTURB_GPU_OK && stream == nullptr) {
             status_ = perturb_gpu_synchronize(handle_);
-        }
-        if (status_ != PERTURB_GPU_OK) {
-            return status_;
-        }
-        scatter(posvel, codes, m, svs, errs);
-        for (std::size_t i = 0; i < n_; ++i) {
-            for (std::size_t k = 0; k < m; ++k) {
-                svs[i * m + k].epoch = epoch(i) + (mins[k] / 1440.0);  // perturb.cpp:229
-            }
         }
         return status_;
     }
@@ -247,23 +236,71 @@ private:
         }
     }
 
-    void scatter(
-        const std::vector<double> &posvel, const std::vector<std::int32_t> &codes,
-        std::size_t m, StateVector *svs, Sgp4Error *errs
-    ) const {
-        const std::size_t plane = n_ * m;
-        for (std::size_t e = 0; e < plane; ++e) {
-            const std::int32_t code = codes[e];
-            if (errs != nullptr) {
-                errs[e] = static_cast<Sgp4Error>(code);
+    // `StateVector` / `Sgp4Error` are handed to the C ABI as they are.
+    static_assert(sizeof(StateVector) == sizeof(perturb_gpu_state), "StateVector is 64 bytes");
+    static_assert(sizeof(JulianDate) == 2 * sizeof(double), "JulianDate is {jd, jd_frac}");
+    static_assert(sizeof(Sgp4Error) == sizeof(std::int32_t), "Sgp4Error is an int enum");
+
+    int propagate_records(
+        const double *ta, const double *tb, std::size_t m, StateVector *svs, Sgp4Error *errs
+    ) {
+        if (n_ == 0 || m == 0) {
+            return status_ = PERTURB_GPU_OK;
+        }
+        std::vector<Sgp4Error> own_errs;
+        if (errs == nullptr) {
+            own_errs.resize(n_ * m);
+            errs = own_errs.data();
+        }
+        // rows with an evaluation that is not NONE (rare: decays, bad elements)
+        std::vector<perturb_gpu_summary> summary(n_);
+        status_ = perturb_gpu_propagate_summary(handle_, ta, tb, m, summary.data(), nullptr);
+        if (status_ == PERTURB_GPU_OK) {
+            status_ = perturb_gpu_synchronize(handle_);
+        }
+        if (status_ != PERTURB_GPU_OK) {
+            return status_;
+        }
+        std::vector<std::size_t> rows;
+        for (std::size_t i = 0; i < n_; ++i) {
+            if (static_cast<std::size_t>(summary[i].n_ok) != m) {
+                rows.push_back(i);
             }
-            if (code == 0 || code == 6) {  // the reference writes r, v for NONE and DECAYED only
-                for (std::size_t c = 0; c < 3; ++c) {
-                    svs[e].position[c] = posvel[c * plane + e];
-                    svs[e].velocity[c] = posvel[(c + 3) * plane + e];
+        }
+        std::vector<StateVector> saved(rows.size() * m);
+        for (std::size_t r = 0; r < rows.size(); ++r) {
+            for (std::size_t k = 0; k < m; ++k) {
+                saved[r * m + k] = svs[rows[r] * m + k];
+            }
+        }
+        std::vector<StateVector> bounce;  // only if the caller's array is not 16-byte aligned
+        StateVector *dst = svs;
+        if ((reinterpret_cast<std::uintptr_t>(svs) & 15u) != 0) {
+            bounce.resize(n_ * m + 1);
+            dst = bounce.data();
+            if ((reinterpret_cast<std::uintptr_t>(dst) & 15u) != 0) {
+                dst = reinterpret_cast<StateVector *>(reinterpret_cast<char *>(dst) + 8);
+            }
+        }
+        if (propagate_states(ta, tb, m, dst, errs, m, nullptr) != PERTURB_GPU_OK) {
+            return status_;
+        }
+        if (dst != svs) {
+            for (std::size_t e = 0; e < n_ * m; ++e) {
+                svs[e] = dst[e];
+            }
+        }
+        for (std::size_t r = 0; r < rows.size(); ++r) {
+            for (std::size_t k = 0; k < m; ++k) {
+                const std::size_t e = rows[r] * m + k;
+                const int code = static_cast<int>(errs[e]);
+                if (code != 0 && code != 6) {  // the reference writes r, v for NONE and DECAYED only
+                    svs[e].position = saved[r * m + k].position;
+                    svs[e].velocity = saved[r * m + k].velocity;
                 }
             }
         }
+        return status_;
     }
 
     perturb_gpu_batch *handle_;

@@ -136,6 +136,28 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
                                      double *posvel, int32_t *err, size_t row_stride,
                                      size_t plane_stride, void *stream);
 
+/* The same two calls writing `perturb::StateVector` records (include/perturb/perturb.hpp:
+ * 198-205: JulianDate epoch {jd, jd_frac}; Vec3 position; Vec3 velocity -- 8 doubles, 64 bytes,
+ * layout asserted in include/perturb/satellite_batch.hpp) instead of structure-of-arrays planes:
+ * the buffer a caller's `std::vector<StateVector>` already is.
+ *   states  states[i * row_stride + k] (row_stride in records, >= m), host or device memory,
+ *           16-byte aligned, satellites in caller order
+ *   err     err[i * row_stride + k]
+ * `epoch` is always set, as the reference does: to (jd[k], jd_frac[k]) by `propagate`
+ * (perturb.cpp:240), to epoch(i) + mins[k] / 1440 (operator+, perturb.cpp:85-89: added to the
+ * fractional part, not normalised) by `propagate_from_epoch` (perturb.cpp:229); jd_frac == NULL
+ * selects that form with `jd` holding minutes. Position and velocity are quiet NaN for error
+ * codes 1-4, where the reference leaves the caller's record untouched. */
+typedef struct perturb_gpu_state {
+    double epoch_jd, epoch_jd_frac;
+    double position[3];
+    double velocity[3];
+} perturb_gpu_state;
+
+int perturb_gpu_propagate_states(perturb_gpu_batch *batch, const double *jd,
+                                 const double *jd_frac, size_t m, perturb_gpu_state *states,
+                                 int32_t *err, size_t row_stride, void *stream);
+
 /* Same evaluation, additionally handing back what `sgp4()` leaves in `Satellite::sat_rec` on
  * every call (src/sgp4.cpp:1895-1901): the singly averaged mean elements
  *     elements[e * plane_stride + i * row_stride + k],  e = am, em, im, Om, om, mm, nm

@@ -267,6 +267,27 @@ class SatelliteBatch:
             self.synchronize()
         return posvel, err
 
+    # perturb::StateVector (perturb.hpp:198-205): JulianDate epoch; Vec3 position; Vec3 velocity
+    STATE_DTYPE = np.dtype([("epoch_jd", "f8"), ("epoch_jd_frac", "f8"), ("position", "f8", 3),
+                            ("velocity", "f8", 3)])
+
+    def propagate_states(self, jd, jd_frac=None, states=None, err=None, stream=None, sync=True):
+        """propagate (or propagate_from_epoch when jd_frac is None, jd = minutes) into an array
+        of 64-byte perturb::StateVector records: returns (states [n, m] STATE_DTYPE, err [n, m]).
+        `states` / `err` may be given: numpy arrays (host, STATE_DTYPE / int32) or CUDA torch
+        tensors (float64 [n, m, 8] / int32 [n, m])."""
+        m = int(jd.shape[0])
+        if states is None:
+            states = np.empty((self.n, m), dtype=self.STATE_DTYPE)
+            err = np.empty((self.n, m), dtype=np.int32)
+        row = int(states.stride(0) // 8) if hasattr(states, "is_cuda") else int(states.strides[0] // 64)
+        st = capi.lib().perturb_gpu_propagate_states(
+            self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(states), _ptr(err), row, stream)
+        capi.check(st, "perturb_gpu_propagate_states")
+        if sync:
+            self.synchronize()
+        return states, err
+
     def propagate_elements(self, jd, jd_frac=None, stream=None):
         """propagate (or propagate_from_epoch when jd_frac is None, jd = minutes) that also
         returns the mean elements sgp4() leaves in sat_rec: (posvel [6,n,m], err [n,m],

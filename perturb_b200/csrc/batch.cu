@@ -409,7 +409,9 @@ int ensure_times(perturb_gpu_batch *b, size_t m) {
     return PERTURB_GPU_OK;
 }
 
-int ensure_stage(perturb_gpu_batch *b, int which, size_t evals) {
+int ensure_stage(perturb_gpu_batch *b, int which, size_t evals, size_t doubles_per_eval = 6) {
+    // capacity is kept in units of 6-double evaluations (the SoA planes); records need 8
+    evals = (evals * doubles_per_eval + 5) / 6;
     if (b->stage_cap[which] >= evals) return PERTURB_GPU_OK;
     cudaFree(b->d_stage[which]);
     cudaFree(b->d_stage_err[which]);
@@ -449,15 +451,21 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
 
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
                    size_t m, double *posvel, int32_t *err, size_t row_stride,
-                   size_t plane_stride, void *stream_arg, double *elements = nullptr) {
+                   size_t plane_stride, void *stream_arg, double *elements = nullptr,
+                   bool records = false) {
+    // records: `posvel` is an array of perturb_gpu_state (8 doubles each) indexed
+    // [sat * row_stride + k]; plane_stride is unused.
     if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
     b->last_launches = 0;
     if (m == 0 || b->n == 0) return PERTURB_GPU_OK;
     if (ta == nullptr || (use_jd && tb == nullptr) || posvel == nullptr || err == nullptr) {
         return fail(PERTURB_GPU_ERR_ARG, "null time or output pointer");
     }
-    if (row_stride < m || plane_stride < b->n * row_stride) {
+    if (row_stride < m || (!records && plane_stride < b->n * row_stride)) {
         return fail(PERTURB_GPU_ERR_ARG, "row_stride < m or plane_stride < n * row_stride");
+    }
+    if (records && (reinterpret_cast<uintptr_t>(posvel) & 15u) != 0) {
+        return fail(PERTURB_GPU_ERR_ARG, "states must be 16-byte aligned");
     }
     if (m > static_cast<size_t>(1) << 30) return fail(PERTURB_GPU_ERR_ARG, "time grid too long");
     DeviceGuard guard(b->device);
@@ -489,6 +497,7 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     fill_launch(b, l);
     l.use_jd = use_jd ? 1 : 0;
     l.elements = elements;
+    l.states = nullptr;
     l.summary_partials = nullptr;
     l.summary_out = nullptr;
     l.n = b->n;
@@ -507,7 +516,8 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         l.ta = d_ta;
         l.tb = d_tb;
         l.m = static_cast<int>(m);
-        l.out = posvel;
+        l.out = records ? nullptr : posvel;
+        l.states = records ? posvel : nullptr;
         l.plane_stride = plane_stride;
         l.row_stride = row_stride;
         l.err = err;
@@ -520,7 +530,8 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     // ---- host outputs: time-chunked, double-buffered device staging + async D2H ----
     size_t free_b = 0, total_b = 0;
     PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t bytes_per_eval = 6 * sizeof(double) + sizeof(int32_t);
+    const size_t dpe = records ? 8 : 6;  // doubles per evaluation in the staging buffer
+    const size_t bytes_per_eval = dpe * sizeof(double) + sizeof(int32_t);
     size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(8) << 30);  // per buffer
     for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * bytes_per_eval);
     const size_t m_even = (m + 1) & ~static_cast<size_t>(1);
@@ -533,7 +544,7 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     const size_t mc_pad = mc;
     const int nbuf = nchunks > 1 ? 2 : 1;
     for (int i = 0; i < nbuf; ++i) {
-        int st = ensure_stage(b, i, b->n * mc_pad);
+        int st = ensure_stage(b, i, b->n * mc_pad, dpe);
         if (st != PERTURB_GPU_OK) return st;
     }
     for (size_t c = 0; c < nchunks; ++c) {
@@ -545,7 +556,8 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         l.ta = d_ta + k0;
         l.tb = use_jd ? d_tb + k0 : nullptr;
         l.m = static_cast<int>(mk);
-        l.out = b->d_stage[buf];
+        l.out = records ? nullptr : b->d_stage[buf];
+        l.states = records ? b->d_stage[buf] : nullptr;
         // one chunk covering whole contiguous caller rows: stage with the caller's own
         // strides so that the D2H is a single linear copy per buffer
         const bool linear = (nchunks == 1) && (row_stride == m) && (m % 2 == 0);
@@ -557,7 +569,24 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaEventRecord(b->ev_done[buf], stream));
         PB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
-        if (linear) {
+        if (records) {
+            // rows of 64-byte records: one 2-D copy (or a linear one when the rows are whole)
+            const size_t rb = 8 * sizeof(double);
+            if (linear) {
+                PB_CUDA(cudaMemcpyAsync(posvel, b->d_stage[buf], b->n * m * rb,
+                                        cudaMemcpyDeviceToHost, b->copy_stream));
+                PB_CUDA(cudaMemcpyAsync(err, b->d_stage_err[buf], b->n * m * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, b->copy_stream));
+            } else {
+                PB_CUDA(cudaMemcpy2DAsync(posvel + k0 * 8, row_stride * rb, b->d_stage[buf],
+                                          mc_pad * rb, mk * rb, b->n, cudaMemcpyDeviceToHost,
+                                          b->copy_stream));
+                PB_CUDA(cudaMemcpy2DAsync(err + k0, row_stride * sizeof(int32_t),
+                                          b->d_stage_err[buf], mc_pad * sizeof(int32_t),
+                                          mk * sizeof(int32_t), b->n, cudaMemcpyDeviceToHost,
+                                          b->copy_stream));
+            }
+        } else if (linear) {
             if (plane_stride == b->n * m) {
                 PB_CUDA(cudaMemcpyAsync(posvel, b->d_stage[buf], 6 * b->n * m * sizeof(double),
                                         cudaMemcpyDeviceToHost, b->copy_stream));
@@ -633,6 +662,15 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
                                      size_t plane_stride, void *stream) {
     return propagate_impl(batch, mins, nullptr, false, m, posvel, err, row_stride, plane_stride,
                           stream);
+}
+
+int perturb_gpu_propagate_states(perturb_gpu_batch *batch, const double *jd,
+                                 const double *jd_frac, size_t m, perturb_gpu_state *states,
+                                 int32_t *err, size_t row_stride, void *stream) {
+    static_assert(sizeof(perturb_gpu_state) == 8 * sizeof(double), "StateVector is 64 bytes");
+    return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m,
+                          reinterpret_cast<double *>(states), err, row_stride, 0, stream, nullptr,
+                          true);
 }
 
 int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,

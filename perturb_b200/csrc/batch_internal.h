@@ -52,6 +52,8 @@ struct PropLaunch {
     int32_t *err;  // err[sat * err_row_stride + k]
     size_t err_row_stride;
     double *elements;  // optional 7 planes am, em, im, Om, om, mm, nm (same strides as out)
+    // array-of-StateVector mode (out unused): 8 doubles per record at (sat * row_stride + k)
+    double *states;
     // fused summary mode (out/err unused): partials [n][chunks], then summary [n]
     void *summary_partials;  // perturb_gpu_summary [n * summary_chunks], scratch
     void *summary_out;       // perturb_gpu_summary [n]

@@ -245,7 +245,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
         double sind, cosd;
         sincos_small<6>(temp, sind, cosd);
-        const double sin_mm = sinm * cosd + cosm * sind;
+        const double sin_mm = mad2(sinm, cosd, cosm, sind);
         tempe = tempe + k(PF_BC5) * (sin_mm - k(PF_SINMAO));
         templ = templ + k(PF_T3COF) * t3 + t4 * (k(PF_T4COF) + t * k(PF_T5COF));
     }
@@ -399,22 +399,22 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         rotate(sinzm, coszm, sd, cd, sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
-        const double ses = k(PF_SE2) * f2 + k(PF_SE3) * f3;
-        const double sis = k(PF_SI2) * f2 + k(PF_SI3) * f3;
-        const double sls = k(PF_SL2) * f2 + k(PF_SL3) * f3 + k(PF_SL4) * sinzf;
-        const double sghs = k(PF_SGH2) * f2 + k(PF_SGH3) * f3 + k(PF_SGH4) * sinzf;
-        const double shs = k(PF_SH2) * f2 + k(PF_SH3) * f3;
+        const double ses = mad2(k(PF_SE2), f2, k(PF_SE3), f3);
+        const double sis = mad2(k(PF_SI2), f2, k(PF_SI3), f3);
+        const double sls = __fma_rn(k(PF_SL4), sinzf, mad2(k(PF_SL2), f2, k(PF_SL3), f3));
+        const double sghs = __fma_rn(k(PF_SGH4), sinzf, mad2(k(PF_SGH2), f2, k(PF_SGH3), f3));
+        const double shs = mad2(k(PF_SH2), f2, k(PF_SH3), f3);
         zm = k(PF_ZMOL) + kMc[MC_ZNL] * t;
         sincos_cw(zm, sinzm, coszm);
         sincos_taylor<4, 5>(kMc[MC_2ZEL] * sinzm, sd, cd);
         rotate(sinzm, coszm, sd, cd, sinzf, coszf);
         f2 = 0.5 * sinzf * sinzf - 0.25;
         f3 = -0.5 * sinzf * coszf;
-        const double sel = k(PF_EE2) * f2 + k(PF_E3) * f3;
-        const double sil = k(PF_XI2) * f2 + k(PF_XI3) * f3;
-        const double sll = k(PF_XL2) * f2 + k(PF_XL3) * f3 + k(PF_XL4) * sinzf;
-        const double sghl = k(PF_XGH2) * f2 + k(PF_XGH3) * f3 + k(PF_XGH4) * sinzf;
-        const double shll = k(PF_XH2) * f2 + k(PF_XH3) * f3;
+        const double sel = mad2(k(PF_EE2), f2, k(PF_E3), f3);
+        const double sil = mad2(k(PF_XI2), f2, k(PF_XI3), f3);
+        const double sll = __fma_rn(k(PF_XL4), sinzf, mad2(k(PF_XL2), f2, k(PF_XL3), f3));
+        const double sghl = __fma_rn(k(PF_XGH4), sinzf, mad2(k(PF_XGH2), f2, k(PF_XGH3), f3));
+        const double shll = mad2(k(PF_XH2), f2, k(PF_XH3), f3);
         // peo, pinco, plo, pgho, pho are zero after dscom (:494-498)
         const double pe = ses + sel;
         const double pinc = sis + sil;
@@ -489,7 +489,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     sincos_cw(argpp, sinargp, cosargp);
     const double axnl = ep * cosargp;
     double temp = rcp_fast(am * (1.0 - ep * ep));
-    const double aynl = ep * sinargp + temp * aycof;
+    const double aynl = mad2(ep, sinargp, temp, aycof);
     const double xl = mp + argpp + nodep + temp * xlcof * axnl;
 
     const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
@@ -538,9 +538,9 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
-    const double ecose = axnl * coseo1 + aynl * sineo1;
-    const double esine = axnl * sineo1 - aynl * coseo1;
-    const double el2 = axnl * axnl + aynl * aynl;
+    const double ecose = mad2(axnl, coseo1, aynl, sineo1);
+    const double esine = msb2(axnl, sineo1, aynl, coseo1);
+    const double el2 = mad2(axnl, axnl, aynl, aynl);
     const double pl = am * (1.0 - el2);
     PB_FAIL_IF(pl < 0.0, 4);  // :1990
 
@@ -576,7 +576,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         x1mth2 = k(PF_X1MTH2);
         x7thm1 = k(PF_X7THM1);
     }
-    const double mrt = rl * (1.0 - 1.5 * temp2 * betal * con41) + 0.5 * temp1 * x1mth2 * cos2u;
+    const double mrt = mad2(rl, 1.0 - 1.5 * temp2 * betal * con41, 0.5 * temp1 * x1mth2, cos2u);
     // The reference forms su = atan2(sinu, cosu) - dsu and then takes sin(su), cos(su)
     // (:2006, 2023, 2031-2032). Only those two are used, so rotate the unit vector
     // (sinu, cosu)/hypot by the small angle dsu instead: no atan2, no second range reduction.
@@ -585,7 +585,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double dxi = 1.5 * temp2 * cosip * sinip * cos2u;  // xinc = xincp + dxi
     const double nmt = nm * temp1 * g.inv_xke;
     const double mvt = rdotl - nmt * x1mth2 * sin2u;
-    const double rvdot = rvdotl + nmt * (x1mth2 * cos2u + 1.5 * con41);
+    const double rvdot = rvdotl + nmt * mad2(x1mth2, cos2u, 1.5, con41);
 
     // ---- orientation vectors, position and velocity, src/sgp4.cpp:2031-2052 ----
     double sinsu, cossu, snod, cnod, sini, cosi;
@@ -597,24 +597,24 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double su_s = sinu, su_c = cosu;
         double sd, cd;
         sincos_small<9>(dsu, sd, cd);
-        sinsu = su_s * cd - su_c * sd;
-        cossu = su_c * cd + su_s * sd;
+        sinsu = msb2(su_s, cd, su_c, sd);
+        cossu = mad2(su_c, cd, su_s, sd);
     }
     sincos_cw(xnode, snod, cnod);
     {
         // xinc = xincp + dxi with dxi ~ 1e-3 and sin/cos(xincp) already at hand
         double sdx, cdx;
         sincos_small<9>(dxi, sdx, cdx);
-        sini = sinip * cdx + cosip * sdx;
-        cosi = cosip * cdx - sinip * sdx;
+        sini = mad2(sinip, cdx, cosip, sdx);
+        cosi = msb2(cosip, cdx, sinip, sdx);
     }
     const double xmx = -snod * cosi;
     const double xmy = cnod * cosi;
-    const double ux = xmx * sinsu + cnod * cossu;
-    const double uy = xmy * sinsu + snod * cossu;
+    const double ux = mad2(xmx, sinsu, cnod, cossu);
+    const double uy = mad2(xmy, sinsu, snod, cossu);
     const double uz = sini * sinsu;
-    const double vx = xmx * cossu - cnod * sinsu;
-    const double vy = xmy * cossu - snod * sinsu;
+    const double vx = msb2(xmx, cossu, cnod, sinsu);
+    const double vy = msb2(xmy, cossu, snod, sinsu);
     const double vz = sini * cossu;
 
     const double mr = mrt * g.radiusearthkm;
@@ -622,9 +622,9 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     out[0] = mr * ux;
     out[1] = mr * uy;
     out[2] = mr * uz;
-    out[3] = mv * ux + rv * vx;
-    out[4] = mv * uy + rv * vy;
-    out[5] = mv * uz + rv * vz;
+    out[3] = mad2(mv, ux, rv, vx);
+    out[4] = mad2(mv, uy, rv, vy);
+    out[5] = mad2(mv, uz, rv, vz);
 
     PB_FAIL_IF(mrt < 1.0, 6);  // :2056
 #undef PB_FAIL_IF

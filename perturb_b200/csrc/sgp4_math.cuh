@@ -299,6 +299,17 @@ __device__ __forceinline__ void sincos_series(double d, double &s, double &c) {
     }
 }
 
+// a b + c d and a b - c d with the contraction spelled out: left to the compiler, which of the
+// two products is fused depends on the code around the expression, and the kernel's output
+// modes (planes, records, mean elements, summary) would then differ from one another in the
+// last bit.
+__device__ __forceinline__ double mad2(double a, double b, double c, double d) {
+    return __fma_rn(a, b, __dmul_rn(c, d));
+}
+__device__ __forceinline__ double msb2(double a, double b, double c, double d) {
+    return __fma_rn(a, b, -__dmul_rn(c, d));
+}
+
 // (sin, cos) of a + d from those of a and of d
 __device__ __forceinline__ void rotate(double sa, double ca, double sd, double cd, double &s,
                                        double &c) {

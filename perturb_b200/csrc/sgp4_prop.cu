@@ -81,6 +81,7 @@ struct PropParams {
     int32_t *err;
     size_t err_row_stride;
     double *elements;
+    double *states;  // perturb_gpu_state [n][row_stride] as doubles (AoS mode)
     perturb_gpu_summary *partials;  // summary mode: [sat * chunks + chunk]
     int chunks;
     GravConsts g;
@@ -208,6 +209,7 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
 constexpr int kModeStates = 0;    // six state planes + error plane
 constexpr int kModeElements = 1;  // ... plus the seven mean-element planes
 constexpr int kModeSummary = 2;   // fused consumer: per-satellite envelope, no [n][m] output
+constexpr int kModeRecords = 3;   // array of 64-byte StateVector records + error plane
 
 struct LaneSummary {
     double r_min, r_max;
@@ -305,7 +307,9 @@ sgp4_prop_kernel(const PropParams p) {
             nodes.k0 = s_k0[s];
             nodes.count = s_cnt[s];
         }
-        double *row = (MODE == kModeSummary) ? nullptr : p.out + static_cast<size_t>(dst) * p.row_stride;
+        double *row = (MODE == kModeSummary)   ? nullptr
+                      : (MODE == kModeRecords) ? p.states + static_cast<size_t>(dst) * p.row_stride * 8
+                                               : p.out + static_cast<size_t>(dst) * p.row_stride;
         int32_t *erow = (MODE == kModeSummary) ? nullptr : p.err + static_cast<size_t>(dst) * p.err_row_stride;
         LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
                            __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
@@ -348,6 +352,27 @@ sgp4_prop_kernel(const PropParams p) {
                         acc.k_err = kt;  // j = 0 precedes j = 1 in time
                         acc.code_err = cd;
                     }
+                }
+            } else if (MODE == kModeRecords) {
+                if (kt < p.m) {
+                    // one perturb::StateVector per lane: 64 contiguous bytes, four 16-byte
+                    // stores; a warp covers 2 KB of the satellite's row
+                    const bool written = (cd == 0) || (cd == 6);
+                    const double tj = (j == 0) ? ta[0] : ta[1];
+                    double2 e;
+                    if (p.use_jd) {
+                        e.x = tj;  // sv.epoch = jd, perturb.cpp:240
+                        e.y = (j == 0) ? tb[0] : tb[1];
+                    } else {
+                        e.x = k(PF_JD0);  // epoch() + mins / 1440, perturb.cpp:229 and :85-89
+                        e.y = __dadd_rn(k(PF_JDF0), __ddiv_rn(tj, 1440.0));
+                    }
+                    double2 *rec = reinterpret_cast<double2 *>(row + static_cast<size_t>(kt) * 8);
+                    rec[0] = e;
+                    rec[1] = make_double2(written ? r[0] : nan, written ? r[1] : nan);
+                    rec[2] = make_double2(written ? r[2] : nan, written ? r[3] : nan);
+                    rec[3] = make_double2(written ? r[4] : nan, written ? r[5] : nan);
+                    erow[kt] = cd;
                 }
             } else if (kt < p.m) {
                 // codes 1-4: the reference leaves the caller's state untouched -> NaN
@@ -433,6 +458,8 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
     }
     if (p.partials != nullptr) {
         sgp4_prop_kernel<CLS, kModeSummary><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+    } else if (p.states != nullptr) {
+        sgp4_prop_kernel<CLS, kModeRecords><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     } else if (p.elements != nullptr) {
         sgp4_prop_kernel<CLS, kModeElements><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     } else {
@@ -469,6 +496,7 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.err = l.err;
     p.err_row_stride = l.err_row_stride;
     p.elements = l.elements;
+    p.states = l.states;
     p.partials = static_cast<perturb_gpu_summary *>(l.summary_partials);
     p.chunks = static_cast<int>(summary_chunks(static_cast<size_t>(l.m)));
     p.g.radiusearthkm = l.radiusearthkm;

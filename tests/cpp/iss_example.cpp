@@ -50,6 +50,7 @@ int main() {
         std::printf("jd %zu err %d r %.17g %.17g %.17g v %.17g %.17g %.17g\n", i,
                     static_cast<int>(errs[i]), sv.position[0], sv.position[1], sv.position[2],
                     sv.velocity[0], sv.velocity[1], sv.velocity[2]);
+        std::printf("jdepoch %zu %.17g %.17g\n", i, sv.epoch.jd, sv.epoch.jd_frac);
     }
 
     const std::vector<double> mins = {0.0, 360.0, 720.0};
@@ -63,6 +64,10 @@ int main() {
                         mins[k], static_cast<int>(err2[i * mins.size() + k]), sv.position[0],
                         sv.position[1], sv.position[2], sv.velocity[0], sv.velocity[1],
                         sv.velocity[2]);
+            // perturb.cpp:229: sv.epoch = epoch() + mins / 1440 (added to the fraction)
+            const JulianDate want = batch.epoch(i) + (mins[k] / 1440.0);
+            std::printf("minsepoch %zu %g %d\n", i, mins[k],
+                        static_cast<int>(sv.epoch.jd == want.jd && sv.epoch.jd_frac == want.jd_frac));
         }
     }
     return 0;

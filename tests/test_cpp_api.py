@@ -55,6 +55,12 @@ def test_cpp_example_matches_reference(tmp_path):
     assert np.abs(r - G["iss_r"]).max() < 1e-6 and np.abs(v - G["iss_v"]).max() < 1e-9
     # rejected TLE: MEAN_MOTION on propagate and the caller's StateVector left untouched
     assert int(jd[3][3]) == 2 and [float(x) for x in jd[3][5:8]] == [-1.0, -1.0, -1.0]
+    # sv.epoch is always set: to the requested JulianDate / to epoch() + mins / 1440, bit for bit
+    ep = [ln.split() for ln in out if ln.startswith("jdepoch")]
+    want_frac = (26.535 + 59 * 60.0 + 1 * 3600.0) / 86400.0
+    assert len(ep) == 4 and all(float(x[2]) == 2459652.5 and float(x[3]) == want_frac for x in ep)
+    mep = [ln.split() for ln in out if ln.startswith("minsepoch")]
+    assert len(mep) == 12 and all(x[3] == "1" for x in mep)
     mins = [ln.split() for ln in out if ln.startswith("mins 1 ")]
     # satellite 00005 with opsmode 'i' (public API); near-Earth, so identical to the 'a' rows
     rows = G["full_i"]

@@ -567,6 +567,54 @@ def test_device_resident_buffers():
     assert b.last_launch_count() >= 5  # one launch per non-empty orbit class + node table
 
 
+def test_statevector_records_equal_the_planes_bit_for_bit():
+    """perturb_gpu_propagate_states: the 64-byte perturb::StateVector records carry exactly the
+    numbers of the structure-of-arrays planes, plus sv.epoch as the reference sets it
+    (perturb.cpp:229 and :240); host and device destinations, odd and strided rows."""
+    import torch
+    L1, L2 = _mixed_batch(1500)
+    # a decaying and a rejected satellite: codes 1-4 leave NaN, epoch still set
+    L1 += [ISS_1[:40]]
+    L2 += [ISS_2]
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    jd, fr = pb.synth_time_grid(333)
+    planes, eplanes = b.propagate(jd, fr)
+    st, est = b.propagate_states(jd, fr)
+    assert st.dtype.itemsize == 64 and np.array_equal(est, eplanes)
+    assert np.array_equal(np.moveaxis(planes[0:3], 0, -1), st["position"], equal_nan=True)
+    assert np.array_equal(np.moveaxis(planes[3:6], 0, -1), st["velocity"], equal_nan=True)
+    assert np.array_equal(st["epoch_jd"], np.broadcast_to(jd, (b.n, jd.size)))
+    assert np.array_equal(st["epoch_jd_frac"], np.broadcast_to(fr, (b.n, jd.size)))
+    assert est[-1, 0] == 2 and np.isnan(st["position"][-1]).all()  # rejected TLE: MEAN_MOTION
+    # minutes form: epoch = epoch(i) + mins / 1440, added to the fraction (perturb.cpp:85-89)
+    mins = np.linspace(-720.0, 4000.0, 97)
+    pm, em = b.propagate_from_epoch(mins)
+    sm, esm = b.propagate_states(mins, None)
+    jd0, fr0 = b.epoch()
+    assert np.array_equal(esm, em)
+    assert np.array_equal(np.moveaxis(pm[0:3], 0, -1), sm["position"], equal_nan=True)
+    assert np.array_equal(sm["epoch_jd"], np.broadcast_to(jd0[:, None], sm.shape))
+    assert np.array_equal(sm["epoch_jd_frac"], fr0[:, None] + (mins / 1440.0)[None, :])
+    # device destination, strided rows, sentinel margin untouched
+    dj, df = torch.tensor(jd, device="cuda"), torch.tensor(fr, device="cuda")
+    wide = torch.full((b.n, 340, 8), -1.0, dtype=torch.float64, device="cuda")
+    ewide = torch.full((b.n, 340), -1, dtype=torch.int32, device="cuda")
+    b.propagate_states(dj, df, wide[:, :333], ewide[:, :333])
+    torch.cuda.synchronize()
+    w = wide.cpu().numpy()
+    assert np.array_equal(w[:, :333].reshape(b.n, 333, 8).view(np.float64),
+                          st.view(np.float64).reshape(b.n, 333, 8), equal_nan=True)
+    assert (w[:, 333:] == -1.0).all() and (ewide.cpu().numpy()[:, 333:] == -1).all()
+    # host destination filled one time-chunk at a time (2-D copies)
+    hw = np.zeros((b.n, 340), dtype=pb.SatelliteBatch.STATE_DTYPE)
+    he = np.full((b.n, 340), -1, dtype=np.int32)
+    for lo, hi in ((0, 100), (100, 101), (101, 333)):
+        b.propagate_states(jd[lo:hi], fr[lo:hi], hw[:, lo:hi], he[:, lo:hi])
+    assert np.array_equal(hw[:, :333].view(np.float64).reshape(b.n, 333, 8),
+                          st.view(np.float64).reshape(b.n, 333, 8), equal_nan=True)
+    assert np.array_equal(he[:, :333], est) and (he[:, 333:] == -1).all()
+
+
 def test_edge_cases_empty_single_and_tile_boundaries():
     l1, l2 = ver_lines(G)
     empty = pb.SatelliteBatch.from_tles([], [])
