@@ -20,6 +20,7 @@
 #ifndef PERTURB_SATELLITE_BATCH_HPP
 #define PERTURB_SATELLITE_BATCH_HPP
 
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <limits>
@@ -308,6 +309,182 @@ private:
     int status_;
     std::vector<std::int32_t> init_error_;
     std::vector<double> epoch_jd_, epoch_frac_;
+};
+
+/// One process, several GPUs: the catalogue is split into contiguous satellite
+/// ranges, one `SatelliteBatch` per device, with no exchange step -- every (satellite, time)
+/// evaluation is independent and the time grid is replicated. Range boundaries balance the
+/// estimated cost (deep-space evaluations cost 1.3-1.8x a near-Earth one), not the count.
+/// A propagate call enqueues on every device first and synchronises afterwards, so with
+/// pinned host buffers (`pinned_alloc`) all devices compute and copy into their slices of the
+/// caller's arrays concurrently. Indices are the caller's, exactly as for `SatelliteBatch`.
+class ShardedSatelliteBatch {
+public:
+    ShardedSatelliteBatch(
+        const TwoLineElement *tles, std::size_t n, const int *devices, std::size_t n_devices,
+        GravModel grav_model = GravModel::WGS72
+    )
+        : n_(n), status_(PERTURB_GPU_OK) {
+        if (n_devices == 0) {
+            status_ = PERTURB_GPU_ERR_ARG;
+            return;
+        }
+        std::vector<double> cost(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            cost[i] = estimated_cost(tles[i]);
+        }
+        cuts_ = plan_ranges(cost, n_devices);
+        for (std::size_t s = 0; s < n_devices; ++s) {
+            shards_.emplace_back(
+                tles + cuts_[s], cuts_[s + 1] - cuts_[s], grav_model, devices[s]
+            );
+            if (!shards_.back().ok()) {
+                status_ = shards_.back().status();
+            }
+        }
+    }
+
+    bool ok() const { return status_ == PERTURB_GPU_OK; }
+    int status() const { return status_; }
+    std::size_t size() const { return n_; }
+    std::size_t shard_count() const { return shards_.size(); }
+    /// Caller indices [begin, end) held by shard `s`.
+    std::size_t shard_begin(std::size_t s) const { return cuts_[s]; }
+    std::size_t shard_end(std::size_t s) const { return cuts_[s + 1]; }
+    SatelliteBatch &shard(std::size_t s) { return shards_[s]; }
+
+    Sgp4Error last_error(std::size_t i) const {
+        const std::size_t s = shard_of(i);
+        return s < shards_.size() ? shards_[s].last_error(i - cuts_[s]) : Sgp4Error::UNKNOWN;
+    }
+    JulianDate epoch(std::size_t i) const {
+        const std::size_t s = shard_of(i);
+        return s < shards_.size() ? shards_[s].epoch(i - cuts_[s]) : JulianDate();
+    }
+
+    /// `SatelliteBatch::propagate_soa` over all shards into HOST buffers indexed by the
+    /// caller's satellite numbers: posvel[c * plane_stride + i * row_stride + k].
+    int propagate_soa(
+        const double *jd, const double *jd_frac, std::size_t m, double *posvel,
+        std::int32_t *err, std::size_t row_stride, std::size_t plane_stride
+    ) {
+        for (std::size_t s = 0; s < shards_.size() && status_ == PERTURB_GPU_OK; ++s) {
+            if (cuts_[s + 1] == cuts_[s]) {
+                continue;
+            }
+            const std::size_t off = cuts_[s] * row_stride;
+            status_ = jd_frac != nullptr
+                ? perturb_gpu_propagate(
+                      shards_[s].handle(), jd, jd_frac, m, posvel + off, err + off, row_stride,
+                      plane_stride, nullptr)
+                : perturb_gpu_propagate_from_epoch(
+                      shards_[s].handle(), jd, m, posvel + off, err + off, row_stride,
+                      plane_stride, nullptr);
+        }
+        return synchronize();
+    }
+
+    /// `SatelliteBatch::propagate_states` over all shards (HOST records, NaN for codes 1-4);
+    /// `jd_frac == nullptr` selects the propagate_from_epoch form with `jd` = minutes.
+    int propagate_states(
+        const double *jd, const double *jd_frac, std::size_t m, StateVector *svs,
+        Sgp4Error *errs, std::size_t row_stride
+    ) {
+        for (std::size_t s = 0; s < shards_.size() && status_ == PERTURB_GPU_OK; ++s) {
+            if (cuts_[s + 1] == cuts_[s]) {
+                continue;
+            }
+            const std::size_t off = cuts_[s] * row_stride;
+            status_ = perturb_gpu_propagate_states(
+                shards_[s].handle(), jd, jd_frac, m,
+                reinterpret_cast<perturb_gpu_state *>(svs + off),
+                reinterpret_cast<std::int32_t *>(errs + off), row_stride, nullptr
+            );
+        }
+        return synchronize();
+    }
+
+    int synchronize() {
+        for (std::size_t s = 0; s < shards_.size(); ++s) {
+            const int st = perturb_gpu_synchronize(shards_[s].handle());
+            if (st != PERTURB_GPU_OK && status_ == PERTURB_GPU_OK) {
+                status_ = st;
+            }
+        }
+        return status_;
+    }
+
+    /// Pinned host memory every device can copy into asynchronously.
+    static void *pinned_alloc(std::size_t bytes) {
+        void *p = nullptr;
+        return perturb_gpu_host_alloc(bytes, &p) == PERTURB_GPU_OK ? p : nullptr;
+    }
+    static void pinned_free(void *p) { perturb_gpu_host_free(p); }
+    static int device_count() {
+        int n = 0;
+        return perturb_gpu_device_count(&n) == PERTURB_GPU_OK ? n : 0;
+    }
+
+    /// Relative cost of one evaluation of this TLE: the flops-v0 weight of the
+    /// orbit class its numbers imply -- sgp4init's thresholds (sgp4.cpp:1590, 773-776, 1516)
+    /// applied to the Kozai mean motion. Used to balance ranges only, never for results.
+    static double estimated_cost(const TwoLineElement &t) {
+        const double two_pi = 6.283185307179586;
+        const double no = t.mean_motion * two_pi / 1440.0;  // rad/min
+        if (!(no > 0.0)) {
+            return 1170.0;
+        }
+        if (two_pi / no >= 225.0) {
+            if (no > 0.0034906585 && no < 0.0052359877) {
+                return 1586.0;  // 24 h resonant
+            }
+            if (no >= 8.26e-3 && no <= 9.24e-3 && t.eccentricity >= 0.5) {
+                return 2097.0;  // 12 h resonant
+            }
+            return 1502.0;
+        }
+        // perigee below 220 km: simplified drag (a = (xke / no)^(2/3) in Earth radii)
+        const double a = std::cbrt(0.0743669161 / no);
+        return a * a * (1.0 - t.eccentricity) < 220.0 / 6378.135 + 1.0 ? 1090.0 : 1170.0;
+    }
+
+    /// Cut points (n_shards + 1 of them, first 0, last n) of the contiguous split whose summed
+    /// costs are as equal as a prefix split allows.
+    static std::vector<std::size_t> plan_ranges(
+        const std::vector<double> &cost, std::size_t n_shards
+    ) {
+        const std::size_t n = cost.size();
+        std::vector<double> cum(n + 1, 0.0);
+        for (std::size_t i = 0; i < n; ++i) {
+            cum[i + 1] = cum[i] + cost[i];
+        }
+        std::vector<std::size_t> cuts(1, 0);
+        for (std::size_t s = 1; s < n_shards; ++s) {
+            const double target = cum[n] * static_cast<double>(s) / static_cast<double>(n_shards);
+            std::size_t k = cuts.back();
+            while (k < n && cum[k + 1] - target < target - cum[k]) {
+                ++k;  // stop at the prefix closest to the target
+            }
+            cuts.push_back(k);
+        }
+        cuts.push_back(n);
+        return cuts;
+    }
+
+private:
+    std::size_t shard_of(std::size_t i) const {
+        for (std::size_t s = 0; s + 1 < cuts_.size(); ++s) {
+            if (i >= cuts_[s] && i < cuts_[s + 1]) {
+                return s;
+            }
+        }
+        return shards_.size();
+    }
+
+    std::size_t n_;
+    int status_;
+    std::vector<std::size_t> cuts_;
+    std::vector<SatelliteBatch> shards_;
 };
 
 }  // namespace perturb

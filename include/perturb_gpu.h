@@ -212,6 +212,17 @@ int perturb_gpu_rv2coe(const double *posvel, size_t n, size_t m, size_t row_stri
 
 int perturb_gpu_synchronize(perturb_gpu_batch *batch);
 
+/* ---- multi-GPU plumbing (one process, several devices) ------------------- */
+
+/* Number of usable CUDA devices. */
+int perturb_gpu_device_count(int *count);
+
+/* Page-locked host memory, visible to every device (cudaHostAllocPortable): with pinned
+ * output buffers a propagate call returns after enqueueing, so shards on several devices run
+ * and copy into their slices of one buffer concurrently. */
+int perturb_gpu_host_alloc(size_t bytes, void **out);
+void perturb_gpu_host_free(void *p);
+
 /* ---- queries ------------------------------------------------------------------------- */
 
 size_t perturb_gpu_size(const perturb_gpu_batch *batch);

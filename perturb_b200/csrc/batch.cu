@@ -757,6 +757,34 @@ int perturb_gpu_synchronize(perturb_gpu_batch *batch) {
     return PERTURB_GPU_OK;
 }
 
+int perturb_gpu_device_count(int *count) {
+    if (count == nullptr) return fail(PERTURB_GPU_ERR_ARG, "count is null");
+    *count = 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(PERTURB_GPU_ERR_NODEV, "no CUDA device available (there is no CPU fallback)");
+    }
+    *count = n;
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_host_alloc(size_t bytes, void **out) {
+    if (out == nullptr) return fail(PERTURB_GPU_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (bytes == 0) return PERTURB_GPU_OK;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(PERTURB_GPU_ERR_ALLOC, "cudaHostAlloc failed");
+    }
+    return PERTURB_GPU_OK;
+}
+
+void perturb_gpu_host_free(void *p) {
+    if (p != nullptr) cudaFreeHost(p);
+}
+
 size_t perturb_gpu_size(const perturb_gpu_batch *batch) { return batch ? batch->n : 0; }
 
 int perturb_gpu_device(const perturb_gpu_batch *batch) { return batch ? batch->device : -1; }

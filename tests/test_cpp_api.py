@@ -15,11 +15,14 @@ SRC = os.path.join(ROOT, "tests", "cpp", "iss_example.cpp")
 REF_INCLUDE = "/root/reference/include"
 
 
-def _compile(tmp_path, extra=()):
-    exe = str(tmp_path / "iss_example")
+SHARDED_SRC = os.path.join(ROOT, "tests", "cpp", "sharded_example.cpp")
+
+
+def _compile(tmp_path, extra=(), src=SRC, name="iss_example"):
+    exe = str(tmp_path / name)
     libdir = os.path.dirname(capi.LIB_PATH)
     cmd = ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
-           *extra, SRC, "-o", exe, "-L" + libdir, "-lperturb_gpu", "-Wl,-rpath," + libdir]
+           *extra, src, "-o", exe, "-L" + libdir, "-lperturb_gpu", "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
     return exe
 
@@ -71,3 +74,67 @@ def test_cpp_example_matches_reference(tmp_path):
         got_v = np.array([float(x) for x in ln[10:13]])
         assert int(ln[4]) == int(ref[2])
         assert np.abs(got_r - ref[3:6]).max() < 1e-6 and np.abs(got_v - ref[6:9]).max() < 1e-9
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
+def test_sharded_header_compiles_as_cxx11_user_code(tmp_path):
+    exe = _compile(tmp_path, src=SHARDED_SRC, name="sharded_example")
+    if not os.path.exists("/dev/nvidia0"):
+        p = subprocess.run([exe], capture_output=True, text=True)
+        assert p.returncode == 2 and "no CPU fallback" in p.stdout  # fails loudly, no fallback
+
+
+def test_cpp_range_plan_matches_the_python_plan(tmp_path):
+    """ShardedSatelliteBatch::plan_ranges / estimated_cost (C++) against perturb_b200.sharding:
+    same class thresholds, cost-balanced contiguous cuts (host logic, no GPU)."""
+    import perturb_b200 as pb
+    n = 4000
+    tl, _ = pb.parse_tle_blocks(*pb.synth_catalog(3, n), n)
+    src = tmp_path / "plan.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include <vector>
+#include <perturb/satellite_batch.hpp>
+int main() {
+    std::vector<double> cost;
+    double mm, ecc;
+    while (std::scanf("%lf %lf", &mm, &ecc) == 2) {
+        perturb::TwoLineElement t = perturb::TwoLineElement();
+        t.mean_motion = mm; t.eccentricity = ecc;
+        cost.push_back(perturb::ShardedSatelliteBatch::estimated_cost(t));
+    }
+    for (double c : cost) std::printf("%.0f\n", c);
+    for (std::size_t k : {1u, 3u, 8u}) {
+        std::printf("cuts");
+        for (std::size_t c : perturb::ShardedSatelliteBatch::plan_ranges(cost, k)) std::printf(" %zu", c);
+        std::printf("\n");
+    }
+    return 0;
+}
+""")
+    exe = str(tmp_path / "plan")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           "-L" + libdir, "-lperturb_gpu", "-Wl,-rpath," + libdir])
+    feed = "".join("%.17g %.17g\n" % (t.mean_motion, t.eccentricity) for t in tl)
+    out = subprocess.run([exe], input=feed, capture_output=True, text=True, check=True).stdout.split("\n")
+    cost = np.array([float(x) for x in out[:n]])
+    want = np.array(pb.sharding.CLASS_COST)[pb.estimate_class(tl)]
+    assert np.array_equal(cost, want)
+    for line, k in zip(out[n:n + 3], (1, 3, 8)):
+        cuts = [int(x) for x in line.split()[1:]]
+        assert cuts[0] == 0 and cuts[-1] == n and len(cuts) == k + 1 and cuts == sorted(cuts)
+        sums = np.array([want[a:b].sum() for a, b in zip(cuts, cuts[1:])])
+        assert sums.max() - sums.min() <= 2 * 2097.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shards", [1, 3, 8])
+def test_cpp_sharded_batch_equals_the_unsharded_one(tmp_path, shards):
+    exe = _compile(tmp_path, src=SHARDED_SRC, name="sharded_example")
+    out = subprocess.run([exe, str(shards)], capture_output=True, text=True, check=True).stdout
+    assert "init_mismatches 0" in out, out
+    assert "planes_equal 1 codes_equal 1" in out, out
+    assert "records_equal 1 record_codes_equal 1 status 0" in out, out
+    cuts = [int(x) for x in out.splitlines()[0].split("cuts")[1].split()]
+    assert len(cuts) == shards and cuts[-1] == 3000
