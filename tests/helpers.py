@@ -110,3 +110,21 @@ def compare_states(err, pos, vel, ref_err, ref_pos, ref_vel, sens_r=None, sens_v
 def posvel_to_rv(posvel):
     """[6, n, m] planes -> pos [n, m, 3], vel [n, m, 3]."""
     return np.moveaxis(posvel[0:3], 0, -1), np.moveaxis(posvel[3:6], 0, -1)
+
+
+def tle_checksum(line68):
+    return str(sum(int(c) if c.isdigit() else (1 if c == "-" else 0) for c in line68) % 10)
+
+
+def make_tle(satnum, epoch_year2, epoch_day, inc_deg, raan_deg, ecc, argp_deg, ma_deg, n_revday,
+             bstar_mantissa=0, bstar_exp=0):
+    """69-column TLE text (valid checksums) from orbital elements in TLE units; B* is
+    0.<mantissa:05d> x 10^<exp>."""
+    bs = "%s%05d%s%d" % ("-" if bstar_mantissa < 0 else " ", abs(bstar_mantissa),
+                         "-" if bstar_exp <= 0 else "+", abs(bstar_exp))
+    l1 = "1 %05dU 20001A   %02d%012.8f  .00000000  00000-0 %s 0  999" % (
+        satnum, epoch_year2, epoch_day, bs)
+    l2 = "2 %05d %8.4f %8.4f %07d %8.4f %8.4f %11.8f%5d" % (
+        satnum, inc_deg, raan_deg, int(round(ecc * 1e7)), argp_deg, ma_deg, n_revday, 1)
+    assert len(l1) == 68 and len(l2) == 68, (len(l1), len(l2))
+    return l1 + tle_checksum(l1), l2 + tle_checksum(l2)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import perturb_b200 as pb
-from helpers import (ISS_1, ISS_2, SENS_GAIN, TOL_POS_KM, compare_states, load_synth_golden, load_ver_golden,
+from helpers import (ISS_1, ISS_2, SENS_GAIN, TOL_POS_KM, compare_states, load_synth_golden, load_ver_golden, make_tle,
                      oracle_sensitivity_jd, oracle_sensitivity_mins, posvel_to_rv, ver_lines)
 from oracle import port
 
@@ -240,6 +240,40 @@ def test_resonant_node_table_long_negative_and_unsorted_spans():
     part, epart = b.propagate_from_epoch(mins[100:140])
     assert np.array_equal(full[:, :, 100:140], part, equal_nan=True)
     assert np.array_equal(efull[:, 100:140], epart)
+
+
+def test_lyddane_branch_down_to_the_equator():
+    """dpper's Lyddane branch (inclination < 0.2 rad, sgp4.cpp:325-364) is evaluated here as
+    node + atan(ph / (sin i + pinc cos i)) with a polynomial arctangent for small ratios and a
+    general atan2 otherwise: geostationary and Molniya-period orbits from exactly equatorial
+    (where the ratio is anything and sin i + pinc cos i changes sign) up to the 11.46 degree
+    switch, both opsmodes, against the oracle."""
+    incs = [0.0, 0.0001, 0.0005, 0.002, 0.01, 0.05, 0.3, 1.0, 5.0, 11.3, 11.45, 11.46, 11.47, 12.0]
+    L1, L2 = [], []
+    k = 0
+    for n_rev, ecc in ((1.00273, 0.0002), (1.0051, 0.05), (2.0057, 0.011), (3.3, 0.2)):
+        for inc in incs:
+            for raan in (0.0, 77.7, 181.0, 359.9):
+                k += 1
+                a, b = make_tle(k, 26, 274.0 + (k % 7) * 0.37, inc, raan, ecc, (53.0 * k) % 360.0,
+                                (211.0 * k) % 360.0, n_rev)
+                L1.append(a)
+                L2.append(b)
+    jd, fr = pb.synth_time_grid(10080)
+    sel = np.linspace(0, 10079, 337).astype(int)
+    for ops in ("i", "a"):
+        b = pb.SatelliteBatch.from_tles(L1, L2, pb.WGS72, ops)
+        orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, ops, flavor=1)
+        assert np.array_equal(b.last_error(), orc.init_error) and (orc.init_error == 0).all()
+        assert set(np.unique(b.orbit_class()).tolist()) == {2, 3}
+        pv, err = b.propagate(jd[sel], fr[sel])
+        pos, vel = posvel_to_rv(pv)
+        eo, ro, vo, _ = orc.propagate_grid(jd[sel], fr[sel], use_jd=True, nthreads=8)
+        sr, sv = oracle_sensitivity_jd(orc, jd[sel], fr[sel])
+        stats = compare_states(err, pos, vel, eo, ro, vo, sr, sv, "Lyddane ops=" + ops)
+        print(stats)
+        assert stats["regular"] > 0.5 * err.size
+        assert stats["max_dr_regular"] < 1e-6 and stats["max_dv_regular"] < 1e-9
 
 
 def test_long_horizons_years_from_epoch():
