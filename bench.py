@@ -348,6 +348,20 @@ def run_gpu(args):
         _ = int(h_err[0, 0])
     e2e_s = time.perf_counter() - te
     e2e_value = float(n) * me * world * e2e_steps / pb.max_over_ranks(e2e_s, dist, dev)
+    # ---- the same through perturb_gpu_propagate_states: the caller's StateVector[n * m] ----
+    del h_out
+    h_states = torch.empty((n, me, 8), dtype=torch.float64).pin_memory()
+    batch.propagate_states(h_jd, h_fr, h_states, h_err)  # warm-up (staging buffers)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    tr = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.propagate_states(h_jd, h_fr, h_states, h_err)  # synchronises
+        _ = int(h_err[0, 0])
+    rec_s = time.perf_counter() - tr
+    rec_value = float(n) * me * world * e2e_steps / pb.max_over_ranks(rec_s, dist, dev)
+    del h_states
     # ---- the fused consumer (N3): host time grid in, one 40-byte summary per satellite out ----
     hs_jd = torch.tensor(jd).pin_memory()
     hs_fr = torch.tensor(fr).pin_memory()
@@ -455,6 +469,15 @@ def run_gpu(args):
             "steps": e2e_steps,
             "host_buffers": "pinned",
             "placement": numa,
+        },
+        "e2e_states": {
+            "value": rec_value,
+            "unit": "evals/s",
+            "what": "perturb_gpu_propagate_states: host time grid in, the caller's array of "
+                    "64-byte perturb::StateVector records + error codes out (pinned host)",
+            "h2d_bytes_per_step": int(2 * me * 8),
+            "d2h_bytes_per_step": int(float(n) * me * 68),
+            "steps": e2e_steps,
         },
         "e2e_summary": {
             "value": sum_value,

@@ -10,7 +10,8 @@
  *   perturb::Sgp4Error       include/perturb/perturb.hpp:50-60   (same enumerators, values)
  *   perturb::GravModel       include/perturb/perturb.hpp:69-73
  *   perturb::Vec3            include/perturb/perturb.hpp:35
- *   perturb::JulianDate      include/perturb/perturb.hpp:117-191 (jd, jd_frac; operator-)
+ *   perturb::DateTime        include/perturb/perturb.hpp:95-102
+ *   perturb::JulianDate      include/perturb/perturb.hpp:117-191 (jd, jd_frac; DateTime ctor, operator-)
  *   perturb::StateVector     include/perturb/perturb.hpp:198-205
  *   perturb::TwoLineElement  include/perturb/tle.hpp:65-91       (numeric members the path reads)
  */
@@ -24,6 +25,7 @@
 #ifndef PERTURB_PERTURB_HPP  // the reference's own include guard
 
 #include <array>
+#include <cmath>
 #include <cstddef>
 
 namespace perturb {
@@ -44,11 +46,33 @@ enum class Sgp4Error : int {
 
 enum class GravModel { WGS72_OLD, WGS72, WGS84 };
 
+struct DateTime {
+    int year;    ///< 1900 .. 2100
+    int month;   ///< 1 .. 12
+    int day;     ///< 1 .. 31
+    int hour;    ///< 0 .. 23
+    int min;     ///< 0 .. 59
+    double sec;  ///< 0.0 .. 59.999...
+};
+
 struct JulianDate {
     double jd;
     double jd_frac;
 
     JulianDate() : jd(0), jd_frac(0) {}
+    /// Calendar date to (whole day at midnight, fraction of day): the arithmetic of
+    /// sgp4::jday_SGP4 (sgp4.cpp:3100-3121), which the reference's constructor calls
+    /// (perturb.cpp:47-52), operation for operation.
+    explicit JulianDate(DateTime t) {
+        jd = 367.0 * t.year - std::floor((7 * (t.year + std::floor((t.month + 9) / 12.0))) * 0.25) +
+             std::floor(275 * t.month / 9.0) + t.day + 1721013.5;
+        jd_frac = (t.sec + t.min * 60.0 + t.hour * 3600.0) / 86400.0;
+        if (std::fabs(jd_frac) > 1.0) {
+            const double whole = std::floor(jd_frac);
+            jd = jd + whole;
+            jd_frac = jd_frac - whole;
+        }
+    }
     explicit JulianDate(double _jd) : jd(_jd), jd_frac(0) {}
     explicit JulianDate(double _jd, double _jd_frac) : jd(_jd), jd_frac(_jd_frac) {}
 

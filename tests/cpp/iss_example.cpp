@@ -32,9 +32,8 @@ int main() {
                     batch.epoch(i).jd_frac);
     }
 
-    // JulianDate(DateTime{2022, 3, 14, 1, 59, 26.535}), as in the reference's example
-    const std::vector<JulianDate> times = {
-        JulianDate(2459652.5, (26.535 + 59 * 60.0 + 1 * 3600.0) / 86400.0)};
+    // as in the reference's example (examples/cmake-local/main.cpp:21)
+    const std::vector<JulianDate> times = {JulianDate(DateTime{2022, 3, 14, 1, 59, 26.535})};
     std::vector<StateVector> svs(batch.size() * times.size());
     for (auto &sv : svs) {
         sv.position = {{-1.0, -1.0, -1.0}};  // must stay untouched on errors 1-4
