@@ -22,6 +22,11 @@
  * Buffers may be host or device pointers (detected with cudaPointerGetAttributes). Device
  * outputs are written directly by the kernel; host outputs go through a device staging
  * buffer owned by the handle and an asynchronous D2H copy (pinned host memory recommended).
+ * A device output buffer may live on ANOTHER GPU of the same process (device-resident gather
+ * of a sharded catalogue): the kernel then stores its satellites' rows into the
+ * peer's memory over NVLink while it computes -- peer access is enabled on first use, and the
+ * call fails with PERTURB_GPU_ERR_ARG if the two devices are not peers. A time grid that
+ * lives on another device is copied to the batch's device first.
  * There is no CPU fallback: without a CUDA device every entry point fails.
  */
 #ifndef PERTURB_GPU_H

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <string>
 #include <vector>
@@ -45,6 +46,45 @@ bool is_device_pointer(const void *p) {
         return false;
     }
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// Ordinal of the device whose memory `p` points into; -1 for host (or managed) memory.
+int pointer_device(const void *p) {
+    if (p == nullptr) return -1;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return attr.type == cudaMemoryTypeDevice ? attr.device : -1;
+}
+
+// A device buffer the kernels of `device` can read in place: its own memory or managed memory.
+bool is_local_device_pointer(const void *p, int device) {
+    if (!is_device_pointer(p)) return false;
+    const int owner = pointer_device(p);
+    return owner < 0 || owner == device;
+}
+
+// Kernels of `device` (the current device) are about to store into a buffer that lives on
+// `owner`: a shard writing its satellite rows straight into the gathered result on another
+// GPU of the same process, over NVLink peer access. Enabled on first use.
+int ensure_peer_access(int device, int owner) {
+    if (owner < 0 || owner == device) return PERTURB_GPU_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, owner) != cudaSuccess || !can) {
+        cudaGetLastError();
+        return fail(PERTURB_GPU_ERR_ARG, "output buffer lives on device " + std::to_string(owner) +
+                                             ", which device " + std::to_string(device) +
+                                             " cannot access as a peer");
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        return fail(PERTURB_GPU_ERR_CUDA,
+                    std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    }
+    cudaGetLastError();
+    return PERTURB_GPU_OK;
 }
 
 // getgravconst, src/sgp4.cpp:2101-2157
@@ -475,20 +515,21 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     b->last_stream = stream;
 
     // ---- time grid on the device ----
-    const bool ta_dev = is_device_pointer(ta);
-    const bool tb_dev = use_jd ? is_device_pointer(tb) : true;
+    // (a grid that lives on another device is copied like a host one: it is read n / 32 times)
+    const bool ta_dev = is_local_device_pointer(ta, b->device);
+    const bool tb_dev = use_jd ? is_local_device_pointer(tb, b->device) : true;
     const double *d_ta = ta, *d_tb = tb;
     if (!ta_dev || !tb_dev) {
         int st = ensure_times(b, m);
         if (st != PERTURB_GPU_OK) return st;
         if (!ta_dev) {
-            PB_CUDA(cudaMemcpyAsync(b->d_times, ta, m * sizeof(double), cudaMemcpyHostToDevice,
+            PB_CUDA(cudaMemcpyAsync(b->d_times, ta, m * sizeof(double), cudaMemcpyDefault,
                                     stream));
             d_ta = b->d_times;
         }
         if (use_jd && !tb_dev) {
-            PB_CUDA(cudaMemcpyAsync(b->d_times + m, tb, m * sizeof(double),
-                                    cudaMemcpyHostToDevice, stream));
+            PB_CUDA(cudaMemcpyAsync(b->d_times + m, tb, m * sizeof(double), cudaMemcpyDefault,
+                                    stream));
             d_tb = b->d_times + m;
         }
     }
@@ -513,6 +554,12 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     }
 
     if (out_dev) {
+        // device-resident gather: the buffers may belong to another GPU of this process
+        for (const void *q : {static_cast<const void *>(posvel), static_cast<const void *>(err),
+                              static_cast<const void *>(elements)}) {
+            const int st = ensure_peer_access(b->device, pointer_device(q));
+            if (st != PERTURB_GPU_OK) return st;
+        }
         l.ta = d_ta;
         l.tb = d_tb;
         l.m = static_cast<int>(m);
@@ -697,19 +744,19 @@ int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const 
     b->last_stream = stream;
 
     const double *d_ta = jd, *d_tb = jd_frac;
-    const bool ta_dev = is_device_pointer(jd);
-    const bool tb_dev = use_jd ? is_device_pointer(jd_frac) : true;
+    const bool ta_dev = is_local_device_pointer(jd, b->device);
+    const bool tb_dev = use_jd ? is_local_device_pointer(jd_frac, b->device) : true;
     if (!ta_dev || !tb_dev) {
         int st = ensure_times(b, m);
         if (st != PERTURB_GPU_OK) return st;
         if (!ta_dev) {
-            PB_CUDA(cudaMemcpyAsync(b->d_times, jd, m * sizeof(double), cudaMemcpyHostToDevice,
+            PB_CUDA(cudaMemcpyAsync(b->d_times, jd, m * sizeof(double), cudaMemcpyDefault,
                                     stream));
             d_ta = b->d_times;
         }
         if (use_jd && !tb_dev) {
             PB_CUDA(cudaMemcpyAsync(b->d_times + m, jd_frac, m * sizeof(double),
-                                    cudaMemcpyHostToDevice, stream));
+                                    cudaMemcpyDefault, stream));
             d_tb = b->d_times + m;
         }
     }
@@ -726,6 +773,10 @@ int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const 
     perturb_gpu_summary *partials = static_cast<perturb_gpu_summary *>(b->d_summary);
     perturb_gpu_summary *folded = partials + b->n * chunks;
     const bool out_dev = is_device_pointer(out);
+    if (out_dev) {
+        const int st = ensure_peer_access(b->device, pointer_device(out));
+        if (st != PERTURB_GPU_OK) return st;
+    }
 
     pb::PropLaunch l;
     fill_launch(b, l);

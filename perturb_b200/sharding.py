@@ -116,8 +116,11 @@ class ShardedSatelliteBatch:
         return np.concatenate([b.orbit_class() for b in self.batches]) if self.n else np.zeros(0, np.uint8)
 
     def propagate(self, jd, jd_frac, posvel=None, err=None):
-        """All shards enqueue first (each into its row range of the shared host buffers),
-        then all are synchronised: devices run and copy concurrently."""
+        """All shards enqueue first (each into its row range of the shared buffers), then all
+        are synchronised: devices run and copy concurrently. `posvel` / `err` may be host arrays
+        (numpy / pinned torch: every device copies its rows in) or CUDA torch tensors on ONE
+        device (device-resident gather: every shard's kernel stores its rows straight into
+        that device's memory over NVLink peer access, no staging and no collective)."""
         m = int(jd.shape[0])
         if posvel is None:
             posvel = np.empty((6, self.n, m), dtype=np.float64)
@@ -129,3 +132,14 @@ class ShardedSatelliteBatch:
         for b in self.batches:
             b.synchronize()
         return posvel, err
+
+    def propagate_to_device(self, jd, jd_frac, device=0):
+        """Device-resident gather: returns (posvel [6, n, m], err [n, m]) as CUDA torch tensors
+        on `device`, every shard having written its own rows there while it computed."""
+        import torch
+        dev = torch.device("cuda", device)
+        m = int(jd.shape[0])
+        posvel = torch.empty((6, self.n, m), dtype=torch.float64, device=dev)
+        err = torch.empty((self.n, m), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)  # the allocator's stream has nothing to do with the shards'
+        return self.propagate(jd, jd_frac, posvel, err)

@@ -120,3 +120,43 @@ def test_sharded_batch_over_available_devices():
     assert np.array_equal(ea, es) and np.array_equal(pa, ps, equal_nan=True)
     assert np.array_equal(whole.last_error(), sharded.last_error())
     assert np.array_equal(whole.orbit_class(), sharded.orbit_class())
+
+
+@pytest.mark.gpu
+def test_device_resident_gather_equals_the_host_gather():
+    """Shards store their rows straight into ONE device's buffers (over NVLink peer access when
+    they sit on other GPUs); the gathered planes equal the unsharded batch bit for bit, with a
+    host or a foreign-device time grid, planes or StateVector records."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) * (2 if ndev == 1 else 1)
+    target = ndev - 1  # not the first shard's device when there are several
+    n = 1100
+    b1, b2 = pb.synth_catalog(3, n)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    whole = pb.SatelliteBatch.from_tles(L1, L2, device=0)
+    sharded = pb.ShardedSatelliteBatch.from_tles(L1, L2, devices)
+    jd, fr = pb.synth_time_grid(130)
+    pa, ea = whole.propagate(jd, fr)
+    pd, ed = sharded.propagate_to_device(jd, fr, device=target)
+    assert pd.device.index == target and ed.device.index == target
+    assert np.array_equal(ea, ed.cpu().numpy())
+    assert np.array_equal(pa, pd.cpu().numpy(), equal_nan=True)
+    # the time grid itself living on the target device: copied to each shard's device
+    d_jd = torch.tensor(jd, device="cuda:%d" % target)
+    d_fr = torch.tensor(fr, device="cuda:%d" % target)
+    pd2 = torch.full_like(pd, -1.0)
+    ed2 = torch.full_like(ed, -1)
+    torch.cuda.synchronize(target)
+    sharded.propagate(d_jd, d_fr, pd2, ed2)
+    assert torch.equal(ed, ed2) and np.array_equal(pd.cpu().numpy(), pd2.cpu().numpy(), equal_nan=True)
+    # records mode through the same peer path: shard g of the last device writes into `target`
+    last = sharded.batches[-1]
+    lo, hi = sharded.ranges[-1]
+    st = torch.empty((hi - lo, 130, 8), dtype=torch.float64, device="cuda:%d" % (0 if ndev > 1 else target))
+    er = torch.empty((hi - lo, 130), dtype=torch.int32, device=st.device)
+    torch.cuda.synchronize(st.device)
+    last.propagate_states(jd, fr, st, er)
+    assert np.array_equal(er.cpu().numpy(), ea[lo:hi])
+    got = st.cpu().numpy()
+    assert np.array_equal(np.moveaxis(got[:, :, 2:8], 2, 0), pa[:, lo:hi], equal_nan=True)
