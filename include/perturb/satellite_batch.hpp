@@ -362,8 +362,11 @@ public:
         return s < shards_.size() ? shards_[s].epoch(i - cuts_[s]) : JulianDate();
     }
 
-    /// `SatelliteBatch::propagate_soa` over all shards into HOST buffers indexed by the
-    /// caller's satellite numbers: posvel[c * plane_stride + i * row_stride + k].
+    /// `SatelliteBatch::propagate_soa` over all shards into buffers indexed by the caller's
+    /// satellite numbers: posvel[c * plane_stride + i * row_stride + k]. The buffers are
+    /// either HOST memory (pinned recommended: every device copies its rows in concurrently)
+    /// or memory of ONE device (`device_alloc`): the device-resident gather, where each
+    /// shard's kernel stores its rows straight into that device over NVLink peer access.
     int propagate_soa(
         const double *jd, const double *jd_frac, std::size_t m, double *posvel,
         std::int32_t *err, std::size_t row_stride, std::size_t plane_stride
@@ -420,6 +423,16 @@ public:
         return perturb_gpu_host_alloc(bytes, &p) == PERTURB_GPU_OK ? p : nullptr;
     }
     static void pinned_free(void *p) { perturb_gpu_host_free(p); }
+    /// Device memory (the target of a device-resident gather) without linking the CUDA runtime.
+    static void *device_alloc(int device, std::size_t bytes) {
+        void *p = nullptr;
+        return perturb_gpu_device_alloc(device, bytes, &p) == PERTURB_GPU_OK ? p : nullptr;
+    }
+    static void device_free(int device, void *p) { perturb_gpu_device_free(device, p); }
+    /// Blocking copy between any two host / device buffers.
+    static int copy(void *dst, const void *src, std::size_t bytes) {
+        return perturb_gpu_copy(dst, src, bytes);
+    }
     static int device_count() {
         int n = 0;
         return perturb_gpu_device_count(&n) == PERTURB_GPU_OK ? n : 0;

@@ -228,6 +228,14 @@ int perturb_gpu_device_count(int *count);
 int perturb_gpu_host_alloc(size_t bytes, void **out);
 void perturb_gpu_host_free(void *p);
 
+/* Device memory for callers that do not link the CUDA runtime themselves: buffers for
+ * device-resident results (and the target of a device-resident gather: shards on other GPUs
+ * store into it over NVLink peer access). perturb_gpu_copy moves `bytes` between any two of
+ * host / device buffers (cudaMemcpyDefault) and returns when the copy is complete. */
+int perturb_gpu_device_alloc(int device, size_t bytes, void **out);
+void perturb_gpu_device_free(int device, void *p);
+int perturb_gpu_copy(void *dst, const void *src, size_t bytes);
+
 /* ---- queries ------------------------------------------------------------------------- */
 
 size_t perturb_gpu_size(const perturb_gpu_batch *batch);

@@ -28,7 +28,7 @@ class Tle(C.Structure):
 # Every symbol include/perturb_gpu.h and include/perturb_synth.h declare.
 EXPORTS = (
     "perturb_gpu_init perturb_gpu_init_from_text perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
-    "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_states perturb_gpu_propagate_elements perturb_gpu_propagate_summary perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_device_count perturb_gpu_host_alloc perturb_gpu_host_free perturb_gpu_size "
+    "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_states perturb_gpu_propagate_elements perturb_gpu_propagate_summary perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_device_count perturb_gpu_host_alloc perturb_gpu_host_free perturb_gpu_device_alloc perturb_gpu_device_free perturb_gpu_copy perturb_gpu_size "
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles "
@@ -82,6 +82,10 @@ def lib():
     L.perturb_gpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.perturb_gpu_host_free.argtypes = [vp]
     L.perturb_gpu_host_free.restype = None
+    L.perturb_gpu_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.perturb_gpu_device_free.argtypes = [C.c_int, vp]
+    L.perturb_gpu_device_free.restype = None
+    L.perturb_gpu_copy.argtypes = [vp, vp, C.c_size_t]
     L.perturb_gpu_size.argtypes = [vp]
     L.perturb_gpu_size.restype = C.c_size_t
     L.perturb_gpu_device.argtypes = [vp]

@@ -836,6 +836,36 @@ void perturb_gpu_host_free(void *p) {
     if (p != nullptr) cudaFreeHost(p);
 }
 
+int perturb_gpu_device_alloc(int device, size_t bytes, void **out) {
+    if (out == nullptr) return fail(PERTURB_GPU_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (bytes == 0) return PERTURB_GPU_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        cudaGetLastError();
+        return fail(PERTURB_GPU_ERR_NODEV, "cudaSetDevice failed (there is no CPU fallback)");
+    }
+    if (cudaMalloc(out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(PERTURB_GPU_ERR_ALLOC, "cudaMalloc failed");
+    }
+    return PERTURB_GPU_OK;
+}
+
+void perturb_gpu_device_free(int device, void *p) {
+    if (p == nullptr) return;
+    DeviceGuard guard(device);
+    cudaFree(p);
+}
+
+int perturb_gpu_copy(void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return PERTURB_GPU_OK;
+    if (dst == nullptr || src == nullptr) return fail(PERTURB_GPU_ERR_ARG, "null pointer");
+    PB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return PERTURB_GPU_OK;
+}
+
 size_t perturb_gpu_size(const perturb_gpu_batch *batch) { return batch ? batch->n : 0; }
 
 int perturb_gpu_device(const perturb_gpu_batch *batch) { return batch ? batch->device : -1; }

@@ -80,6 +80,25 @@ int main(int argc, char **argv) {
     std::printf("planes_equal %d codes_equal %d\n",
                 std::memcmp(pa, pb, 6 * plane * 8) == 0, std::memcmp(ea, eb, plane * 4) == 0);
 
+    // device-resident gather: the same call with buffers on the LAST device; shards on other
+    // devices store their rows there over NVLink peer access
+    {
+        const int target = n_dev - 1;
+        double *dp = static_cast<double *>(ShardedSatelliteBatch::device_alloc(target, 6 * plane * 8));
+        std::int32_t *de =
+            static_cast<std::int32_t *>(ShardedSatelliteBatch::device_alloc(target, plane * 4));
+        std::memset(pb, 0xff, 6 * plane * 8);
+        std::memset(eb, 0xff, plane * 4);
+        int st = (dp && de) ? sharded.propagate_soa(jd.data(), fr.data(), m, dp, de, m, plane) : -99;
+        if (st == 0) st = ShardedSatelliteBatch::copy(pb, dp, 6 * plane * 8);
+        if (st == 0) st = ShardedSatelliteBatch::copy(eb, de, plane * 4);
+        std::printf("device_gather_equal %d device_gather_codes_equal %d status %d target %d\n",
+                    std::memcmp(pa, pb, 6 * plane * 8) == 0, std::memcmp(ea, eb, plane * 4) == 0, st,
+                    target);
+        ShardedSatelliteBatch::device_free(target, dp);
+        ShardedSatelliteBatch::device_free(target, de);
+    }
+
     std::vector<double> mins(m);
     for (std::size_t k = 0; k < m; ++k) {
         mins[k] = 11.0 * static_cast<double>(k) - 100.0;

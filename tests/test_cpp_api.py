@@ -136,5 +136,6 @@ def test_cpp_sharded_batch_equals_the_unsharded_one(tmp_path, shards):
     assert "init_mismatches 0" in out, out
     assert "planes_equal 1 codes_equal 1" in out, out
     assert "records_equal 1 record_codes_equal 1 status 0" in out, out
+    assert "device_gather_equal 1 device_gather_codes_equal 1 status 0" in out, out
     cuts = [int(x) for x in out.splitlines()[0].split("cuts")[1].split()]
     assert len(cuts) == shards and cuts[-1] == 3000
