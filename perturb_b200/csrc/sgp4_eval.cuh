@@ -177,8 +177,12 @@ __device__ __forceinline__ int resonance_step_count(double t) {
 
 // Integrator states tabulated per satellite by the pre-pass kernel: node j holds (xli, xni)
 // after (k0 + j) steps from epoch (negative = backwards).
+// and the rates (xndt, xnddt) the integrator derives from that state (src/sgp4.cpp:1097-1140):
+// they depend on the node only, so an evaluation that starts AT a tabulated node needs no
+// sin/cos of the resonance angles at all.
 struct ResNodes {
-    const double2 *base;  // this satellite's column: element j at base[j * stride]
+    const double2 *base;   // this satellite's column: element j at base[j * stride]
+    const double2 *rates;  // same indexing: (xndt, xnddt) at node j
     size_t stride;
     int k0, count;
 };
@@ -294,22 +298,33 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
                     }
                 }
             }
+            const int left = (kk >= 0) ? kk - kj : kj - kk;
+            bool have_rates = false;
             if (from_table) {
-                const double2 st = nodes->base[static_cast<size_t>(kj - nodes->k0) * nodes->stride];
+                const size_t at = static_cast<size_t>(kj - nodes->k0) * nodes->stride;
+                const double2 st = nodes->base[at];
                 xli = st.x;
                 xni = st.y;
                 atime = __dmul_rn(720.0, static_cast<double>(kj));
+                if (left == 0) {
+                    // the pre-pass evaluated resonance_rates at this very node with these very
+                    // inputs: same operations, same bits
+                    const double2 rt = nodes->rates[at];
+                    xndt = rt.x;
+                    xnddt = rt.y;
+                    xldot = __dadd_rn(xni, k(PF_XFACT));
+                    have_rates = true;
+                }
             } else {
                 atime = 0.0;
                 xni = no;
                 xli = k(PF_XLAMO);
             }
-            const int left = (kk >= 0) ? kk - kj : kj - kk;
             for (int i = 0; i < left; ++i) {
                 resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
                 resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
             }
-            resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            if (!have_rates) resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
             const double ft = t - atime;
             nm = xni + xndt * ft + xnddt * ft * ft * 0.5;
             const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;

@@ -87,7 +87,8 @@ struct PropParams {
     GravConsts g;
     int opsmode_a;
     // resonance node table (deep-space resonant classes only)
-    const double2 *res_nodes;  // [res_cap][res_stride]
+    const double2 *res_nodes;  // [res_cap][res_stride] (xli, xni)
+    const double2 *res_rates;  // [res_cap][res_stride] (xndt, xnddt)
     const int *res_k0;         // [res_stride] first tabulated step index per resonant slot
     const int *res_cnt;        // [res_stride] number of tabulated nodes
     size_t res_stride;         // resonant slots (padded)
@@ -155,8 +156,8 @@ __global__ void __launch_bounds__(128)
 resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_t *__restrict__ perm,
                        size_t first_slot, int n_slots, int first_r2_slot_rel,
                        const double *__restrict__ range, int use_jd, int cap,
-                       double2 *__restrict__ nodes, int *__restrict__ k0_out,
-                       int *__restrict__ cnt_out) {
+                       double2 *__restrict__ nodes, double2 *__restrict__ rates,
+                       int *__restrict__ k0_out, int *__restrict__ cnt_out) {
     const int rs = blockIdx.x * blockDim.x + threadIdx.x;
     if (rs >= n_slots) return;
     const size_t slot = first_slot + rs;
@@ -187,8 +188,10 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     if (k_end > 0) {
         double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
         for (int kk = 0; kk < k_end; ++kk) {
-            if (kk >= k_lo) nodes[static_cast<size_t>(kk - k_lo) * stride + rs] = make_double2(xli, xni);
+            const size_t at = static_cast<size_t>(kk - k_lo) * stride + rs;
+            if (kk >= k_lo) nodes[at] = make_double2(xli, xni);
             resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            if (kk >= k_lo) rates[at] = make_double2(xndt, xnddt);
             resonance_advance(xndt, xldot, xnddt, 720.0, xli, xni, atime);
         }
     }
@@ -196,10 +199,11 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     if (k_lo < 0) {
         double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
         for (int kk = 0; kk >= k_lo; --kk) {
-            if (kk < k_end && kk <= 0 && !(kk == 0 && k_end > 0)) {
-                nodes[static_cast<size_t>(kk - k_lo) * stride + rs] = make_double2(xli, xni);
-            }
+            const bool keep = kk < k_end && kk <= 0 && !(kk == 0 && k_end > 0);
+            const size_t at = static_cast<size_t>(kk - k_lo) * stride + rs;
+            if (keep) nodes[at] = make_double2(xli, xni);
             resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            if (keep) rates[at] = make_double2(xndt, xnddt);
             resonance_advance(xndt, xldot, xnddt, -720.0, xli, xni, atime);
         }
     }
@@ -300,9 +304,10 @@ sgp4_prop_kernel(const PropParams p) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
         const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
-        ResNodes nodes = {nullptr, 0, 0, 0};
+        ResNodes nodes = {nullptr, nullptr, 0, 0, 0};
         if (kResonant) {
             nodes.base = p.res_nodes + (sat0 + s - p.res_first_slot);
+            nodes.rates = p.res_rates + (sat0 + s - p.res_first_slot);
             nodes.stride = p.res_stride;
             nodes.k0 = s_k0[s];
             nodes.count = s_cnt[s];
@@ -507,7 +512,7 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.g.inv_xke = 1.0 / l.xke;
     p.opsmode_a = l.opsmode_a;
     int launches = 0;
-    p.res_nodes = nullptr;
+    p.res_nodes = p.res_rates = nullptr;
     p.res_k0 = p.res_cnt = nullptr;
     p.res_stride = 0;
     p.res_first_slot = 0;
@@ -519,9 +524,11 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
         resonance_nodes_kernel<<<(n_slots + 127) / 128, 128, 0, stream>>>(
             l.pf, l.n_pad, l.perm, first_slot, n_slots,
             l.tile_count[PB_CLS_DEEP_R1] * PB_TILE_SATS, l.res_range, l.use_jd, l.res_cap,
-            l.res_nodes, l.res_k0, l.res_cnt);
+            l.res_nodes, l.res_nodes + static_cast<size_t>(l.res_cap) * n_slots, l.res_k0,
+            l.res_cnt);
         launches += 2;
         p.res_nodes = l.res_nodes;
+        p.res_rates = l.res_nodes + static_cast<size_t>(l.res_cap) * n_slots;
         p.res_k0 = l.res_k0;
         p.res_cnt = l.res_cnt;
         p.res_stride = static_cast<size_t>(n_slots);
