@@ -159,7 +159,7 @@ struct perturb_gpu_batch {
     int32_t *d_stage_err[2];
     size_t stage_cap[2];  // evaluations each staging buffer holds
     cudaEvent_t ev_done[2], ev_free[2];
-    double2 *d_res_nodes;  // resonance node table [2][res_cap][resonant slots]
+    double2 *d_res_nodes;  // resonance node table [resonant slots][res_cap] of 32-byte records
     int *d_res_k0, *d_res_cnt;
     double *d_res_range;
     int res_cap;
@@ -307,7 +307,8 @@ int finish_create(perturb_gpu_batch *b, double *d_pf_stage, uint8_t *d_cls, int3
                                                  b->tile_count[PB_CLS_DEEP_R2]) * PB_TILE_SATS;
     if (res_slots > 0) {
         size_t cap = 64;
-        // two planes: the integrator state (xli, xni) and its rates (xndt, xnddt) per node
+        // one 32-byte record per node: the integrator state (xli, xni) and its rates (xndt, xnddt)
+        // (at most 2^25 records, so that record indices fit an int with room to spare)
         while (cap > 4 && 2 * cap * res_slots * sizeof(double2) > (static_cast<size_t>(1) << 30)) cap /= 2;
         PB_CUDA(cudaMalloc(&b->d_res_nodes, 2 * cap * res_slots * sizeof(double2)));
         PB_CUDA(cudaMalloc(&b->d_res_k0, res_slots * sizeof(int)));

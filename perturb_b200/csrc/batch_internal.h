@@ -61,7 +61,7 @@ struct PropLaunch {
     double radiusearthkm, xke, j2, j3oj2;
     int opsmode_a;
     // resonance node table scratch (null / 0: resonant evaluations integrate in-line)
-    double2 *res_nodes;  // [2][res_cap][resonant slots]: states, then rates
+    double2 *res_nodes;  // [resonant slots][res_cap] records {xli, xni, xndt, xnddt} (2 double2 each)
     int *res_k0, *res_cnt;
     double *res_range;   // [4]
     int res_cap;

@@ -175,15 +175,17 @@ __device__ __forceinline__ int resonance_step_count(double t) {
     return n;
 }
 
-// Integrator states tabulated per satellite by the pre-pass kernel: node j holds (xli, xni)
-// after (k0 + j) steps from epoch (negative = backwards).
-// and the rates (xndt, xnddt) the integrator derives from that state (src/sgp4.cpp:1097-1140):
-// they depend on the node only, so an evaluation that starts AT a tabulated node needs no
-// sin/cos of the resonance angles at all.
+// Integrator nodes tabulated per satellite by the pre-pass kernel: record j holds the state
+// (xli, xni) after (k0 + j) steps from epoch (negative = backwards) and the rates (xndt, xnddt)
+// the integrator derives from that state (src/sgp4.cpp:1097-1140). The rates depend on the node
+// only, so an evaluation whose node is tabulated needs no sin/cos of the resonance angles at
+// all: one 32-byte record (one sector) instead.
+struct ResNode {
+    double xli, xni, xndt, xnddt;
+};
 struct ResNodes {
-    const double2 *base;   // this satellite's column: element j at base[j * stride]
-    const double2 *rates;  // same indexing: (xndt, xnddt) at node j
-    size_t stride;
+    const ResNode *table;  // all records; this satellite's are [first, first + count)
+    int first;             // record index of this satellite's node k0
     int k0, count;
 };
 
@@ -277,54 +279,57 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             const int kk = (t > 0.0) ? n : -n;
             double atime, xni, xli;
             double xndt, xldot, xnddt;
-            // Start from the tabulated node nearest to step kk on the way from epoch (same
-            // direction, not beyond kk); walk whatever is left in-line. With the whole grid
-            // inside the table this is one 16 B load and no step at all.
-            int kj = 0;  // step index the walk starts from (0 = epoch)
-            bool from_table = false;
-            if (nodes != nullptr && nodes->count > 0) {
-                const int k1 = nodes->k0 + nodes->count - 1;  // last tabulated index
-                if (kk >= 0) {
-                    const int cand = kk < k1 ? kk : k1;
-                    if (cand >= nodes->k0 && cand >= 0) {
-                        kj = cand;
-                        from_table = true;
-                    }
-                } else {
-                    const int cand = kk > nodes->k0 ? kk : nodes->k0;
-                    if (cand <= k1 && cand <= 0) {
-                        kj = cand;
-                        from_table = true;
-                    }
-                }
-            }
-            const int left = (kk >= 0) ? kk - kj : kj - kk;
-            bool have_rates = false;
-            if (from_table) {
-                const size_t at = static_cast<size_t>(kj - nodes->k0) * nodes->stride;
-                const double2 st = nodes->base[at];
-                xli = st.x;
-                xni = st.y;
-                atime = __dmul_rn(720.0, static_cast<double>(kj));
-                if (left == 0) {
-                    // the pre-pass evaluated resonance_rates at this very node with these very
-                    // inputs: same operations, same bits
-                    const double2 rt = nodes->rates[at];
-                    xndt = rt.x;
-                    xnddt = rt.y;
-                    xldot = __dadd_rn(xni, k(PF_XFACT));
-                    have_rates = true;
-                }
+            const int at = (nodes != nullptr) ? kk - nodes->k0 : -1;
+            if (nodes != nullptr && static_cast<unsigned>(at) < static_cast<unsigned>(nodes->count)) {
+                // the step kk itself is tabulated (every time of a grid spanning up to 32 days):
+                // the pre-pass reached it walking from epoch in the same direction and evaluated
+                // resonance_rates there with these very inputs -- same operations, same bits
+                const double4 nd = *reinterpret_cast<const double4 *>(nodes->table + (nodes->first + at));
+                xli = nd.x;
+                xni = nd.y;
+                xndt = nd.z;
+                xnddt = nd.w;
+                xldot = __dadd_rn(xni, k(PF_XFACT));
+                atime = __dmul_rn(720.0, static_cast<double>(kk));
             } else {
-                atime = 0.0;
-                xni = no;
-                xli = k(PF_XLAMO);
-            }
-            for (int i = 0; i < left; ++i) {
+                // Start from the tabulated node nearest to step kk on the way from epoch (same
+                // direction, not beyond kk) or from epoch itself, and walk whatever is left
+                // in-line (kernel 1's epoch probe, times outside the table).
+                int kj = 0;  // step index the walk starts from (0 = epoch)
+                bool from_table = false;
+                if (nodes != nullptr && nodes->count > 0) {
+                    const int k1 = nodes->k0 + nodes->count - 1;  // last tabulated index
+                    if (kk >= 0) {
+                        const int cand = kk < k1 ? kk : k1;
+                        if (cand >= nodes->k0 && cand >= 0) {
+                            kj = cand;
+                            from_table = true;
+                        }
+                    } else {
+                        const int cand = kk > nodes->k0 ? kk : nodes->k0;
+                        if (cand <= k1 && cand <= 0) {
+                            kj = cand;
+                            from_table = true;
+                        }
+                    }
+                }
+                if (from_table) {
+                    const ResNode *nd = nodes->table + (nodes->first + (kj - nodes->k0));
+                    xli = nd->xli;
+                    xni = nd->xni;
+                    atime = __dmul_rn(720.0, static_cast<double>(kj));
+                } else {
+                    atime = 0.0;
+                    xni = no;
+                    xli = k(PF_XLAMO);
+                }
+                const int left = (kk >= 0) ? kk - kj : kj - kk;
+                for (int i = 0; i < left; ++i) {
+                    resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+                    resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
+                }
                 resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
-                resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
             }
-            if (!have_rates) resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
             const double ft = t - atime;
             nm = xni + xndt * ft + xnddt * ft * ft * 0.5;
             const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;

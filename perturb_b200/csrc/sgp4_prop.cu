@@ -87,11 +87,10 @@ struct PropParams {
     GravConsts g;
     int opsmode_a;
     // resonance node table (deep-space resonant classes only)
-    const double2 *res_nodes;  // [res_cap][res_stride] (xli, xni)
-    const double2 *res_rates;  // [res_cap][res_stride] (xndt, xnddt)
-    const int *res_k0;         // [res_stride] first tabulated step index per resonant slot
-    const int *res_cnt;        // [res_stride] number of tabulated nodes
-    size_t res_stride;         // resonant slots (padded)
+    const ResNode *res_nodes;  // [resonant slot][res_cap] node records
+    const int *res_k0;         // [resonant slots] first tabulated step index
+    const int *res_cnt;        // [resonant slots] number of tabulated nodes
+    int res_cap;               // records per resonant slot
     size_t res_first_slot;     // sorted slot of the first resonant satellite
 };
 
@@ -156,8 +155,8 @@ __global__ void __launch_bounds__(128)
 resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_t *__restrict__ perm,
                        size_t first_slot, int n_slots, int first_r2_slot_rel,
                        const double *__restrict__ range, int use_jd, int cap,
-                       double2 *__restrict__ nodes, double2 *__restrict__ rates,
-                       int *__restrict__ k0_out, int *__restrict__ cnt_out) {
+                       ResNode *__restrict__ nodes, int *__restrict__ k0_out,
+                       int *__restrict__ cnt_out) {
     const int rs = blockIdx.x * blockDim.x + threadIdx.x;
     if (rs >= n_slots) return;
     const size_t slot = first_slot + rs;
@@ -182,16 +181,14 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     cnt_out[rs] = count;
     if (count <= 0) return;
     const int k_end = k_lo + count;  // tabulate [k_lo, k_end)
-    const size_t stride = static_cast<size_t>(n_slots);
+    ResNode *mine = nodes + static_cast<size_t>(rs) * cap;
     const double no = k(PF_NO), xlamo = k(PF_XLAMO);
     // forwards from epoch
     if (k_end > 0) {
         double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
         for (int kk = 0; kk < k_end; ++kk) {
-            const size_t at = static_cast<size_t>(kk - k_lo) * stride + rs;
-            if (kk >= k_lo) nodes[at] = make_double2(xli, xni);
             resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
-            if (kk >= k_lo) rates[at] = make_double2(xndt, xnddt);
+            if (kk >= k_lo) mine[kk - k_lo] = {xli, xni, xndt, xnddt};
             resonance_advance(xndt, xldot, xnddt, 720.0, xli, xni, atime);
         }
     }
@@ -199,11 +196,10 @@ resonance_nodes_kernel(const double *__restrict__ pf, size_t n_pad, const int32_
     if (k_lo < 0) {
         double xli = xlamo, xni = no, atime = 0.0, xndt, xldot, xnddt;
         for (int kk = 0; kk >= k_lo; --kk) {
-            const bool keep = kk < k_end && kk <= 0 && !(kk == 0 && k_end > 0);
-            const size_t at = static_cast<size_t>(kk - k_lo) * stride + rs;
-            if (keep) nodes[at] = make_double2(xli, xni);
             resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
-            if (keep) rates[at] = make_double2(xndt, xnddt);
+            if (kk < k_end && kk <= 0 && !(kk == 0 && k_end > 0)) {
+                mine[kk - k_lo] = {xli, xni, xndt, xnddt};
+            }
             resonance_advance(xndt, xldot, xnddt, -720.0, xli, xni, atime);
         }
     }
@@ -251,8 +247,7 @@ sgp4_prop_kernel(const PropParams p) {
     __shared__ double s_tb[kTimeTile];
     __shared__ int s_perm[PB_TILE_SATS];
     constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
-    __shared__ int s_k0[kResonant ? PB_TILE_SATS : 1];
-    __shared__ int s_cnt[kResonant ? PB_TILE_SATS : 1];
+    __shared__ int4 s_res[kResonant ? PB_TILE_SATS : 1];  // {k0, count, first record, -}
 
     const int ttile = blockIdx.x % p.n_time_tiles;
     const int stile = p.tile_begin + blockIdx.x / p.n_time_tiles;
@@ -269,8 +264,8 @@ sgp4_prop_kernel(const PropParams p) {
     if (kResonant && threadIdx.x < PB_TILE_SATS) {
         const size_t rs = sat0 + threadIdx.x - p.res_first_slot;
         const bool have = p.res_nodes != nullptr;
-        s_k0[threadIdx.x] = have ? p.res_k0[rs] : 0;
-        s_cnt[threadIdx.x] = have ? p.res_cnt[rs] : 0;
+        s_res[threadIdx.x] = make_int4(have ? p.res_k0[rs] : 0, have ? p.res_cnt[rs] : 0,
+                                       static_cast<int>(rs) * p.res_cap, 0);
     }
     const int k_base = ttile * kTimeTile;
     for (int i = threadIdx.x; i < kTimeTile; i += kThreads) {
@@ -304,13 +299,13 @@ sgp4_prop_kernel(const PropParams p) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
         const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
-        ResNodes nodes = {nullptr, nullptr, 0, 0, 0};
+        ResNodes nodes = {nullptr, 0, 0, 0};
         if (kResonant) {
-            nodes.base = p.res_nodes + (sat0 + s - p.res_first_slot);
-            nodes.rates = p.res_rates + (sat0 + s - p.res_first_slot);
-            nodes.stride = p.res_stride;
-            nodes.k0 = s_k0[s];
-            nodes.count = s_cnt[s];
+            const int4 rn = s_res[s];
+            nodes.table = p.res_nodes;
+            nodes.k0 = rn.x;
+            nodes.count = rn.y;
+            nodes.first = rn.z;
         }
         double *row = (MODE == kModeSummary)   ? nullptr
                       : (MODE == kModeRecords) ? p.states + static_cast<size_t>(dst) * p.row_stride * 8
@@ -512,9 +507,9 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.g.inv_xke = 1.0 / l.xke;
     p.opsmode_a = l.opsmode_a;
     int launches = 0;
-    p.res_nodes = p.res_rates = nullptr;
+    p.res_nodes = nullptr;
     p.res_k0 = p.res_cnt = nullptr;
-    p.res_stride = 0;
+    p.res_cap = 0;
     p.res_first_slot = 0;
     const int res_tiles = l.tile_count[PB_CLS_DEEP_R1] + l.tile_count[PB_CLS_DEEP_R2];
     if (res_tiles > 0 && l.res_nodes != nullptr && l.res_cap > 0) {
@@ -524,14 +519,12 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
         resonance_nodes_kernel<<<(n_slots + 127) / 128, 128, 0, stream>>>(
             l.pf, l.n_pad, l.perm, first_slot, n_slots,
             l.tile_count[PB_CLS_DEEP_R1] * PB_TILE_SATS, l.res_range, l.use_jd, l.res_cap,
-            l.res_nodes, l.res_nodes + static_cast<size_t>(l.res_cap) * n_slots, l.res_k0,
-            l.res_cnt);
+            reinterpret_cast<ResNode *>(l.res_nodes), l.res_k0, l.res_cnt);
         launches += 2;
-        p.res_nodes = l.res_nodes;
-        p.res_rates = l.res_nodes + static_cast<size_t>(l.res_cap) * n_slots;
+        p.res_nodes = reinterpret_cast<const ResNode *>(l.res_nodes);
+        p.res_cap = l.res_cap;
         p.res_k0 = l.res_k0;
         p.res_cnt = l.res_cnt;
-        p.res_stride = static_cast<size_t>(n_slots);
         p.res_first_slot = first_slot;
     }
     const int prelaunches = launches;
