@@ -388,18 +388,44 @@ sgp4_prop_kernel(const PropParams p) {
             }
         }
         if (MODE == kModeSummary) {
-            // warp reduction over the 64 times of this satellite, then one partial record
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                LaneSummary o;
-                o.r_min = __shfl_down_sync(0xffffffffu, acc.r_min, off);
-                o.r_max = __shfl_down_sync(0xffffffffu, acc.r_max, off);
-                o.k_min = __shfl_down_sync(0xffffffffu, acc.k_min, off);
-                o.k_max = __shfl_down_sync(0xffffffffu, acc.k_max, off);
-                o.n_ok = __shfl_down_sync(0xffffffffu, acc.n_ok, off);
-                o.k_err = __shfl_down_sync(0xffffffffu, acc.k_err, off);
-                o.code_err = __shfl_down_sync(0xffffffffu, acc.code_err, off);
-                merge_summary(acc, o);
+            // Warp reduction over the 64 times of this satellite, then one partial record. The
+            // radii are non-negative doubles, which order like their bit patterns, so min / max
+            // with "ties to the lowest time index" are three 32-bit warp reductions each (high
+            // word, low word among the lanes that match, index among those that match both)
+            // instead of five rounds of seven shuffles and a full merge.
+            {
+                const unsigned full = 0xffffffffu;
+                // minimum radius: lanes without an ok evaluation hold +inf and index -1
+                unsigned hi = static_cast<unsigned>(__double2hiint(acc.r_min));
+                unsigned lo = static_cast<unsigned>(__double2loint(acc.r_min));
+                unsigned m_hi = __reduce_min_sync(full, hi);
+                bool cand = hi == m_hi;
+                unsigned m_lo = __reduce_min_sync(full, cand ? lo : 0xffffffffu);
+                cand = cand && lo == m_lo;
+                unsigned m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(acc.k_min) : 0xffffffffu);
+                acc.r_min = __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo));
+                acc.k_min = static_cast<int>(m_k);
+                // maximum radius: lanes without an ok evaluation (-inf, index -1) count as key 0
+                const bool have = acc.k_max >= 0;
+                hi = have ? static_cast<unsigned>(__double2hiint(acc.r_max)) : 0u;
+                lo = have ? static_cast<unsigned>(__double2loint(acc.r_max)) : 0u;
+                m_hi = __reduce_max_sync(full, hi);
+                cand = hi == m_hi;
+                m_lo = __reduce_max_sync(full, cand ? lo : 0u);
+                cand = cand && lo == m_lo;
+                m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(acc.k_max) : 0xffffffffu);
+                acc.k_max = static_cast<int>(m_k);
+                acc.r_max = (acc.k_max >= 0)
+                                ? __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo))
+                                : __longlong_as_double(0xfff0000000000000LL);
+                acc.n_ok = __reduce_add_sync(full, acc.n_ok);
+                // first error in time: every lane's index is distinct, so one lane matches
+                const unsigned ke = static_cast<unsigned>(acc.k_err);  // -1 -> 0xffffffff
+                const unsigned m_e = __reduce_min_sync(full, ke);
+                const unsigned code = __reduce_max_sync(
+                    full, (ke == m_e && acc.k_err >= 0) ? static_cast<unsigned>(acc.code_err) : 0u);
+                acc.k_err = static_cast<int>(m_e);
+                acc.code_err = static_cast<int>(code);
             }
             if (lane == 0) {
                 perturb_gpu_summary out;
