@@ -10,7 +10,9 @@
 //     branch is warp-uniform, constants are shared-memory broadcasts, and one evaluation of
 //     a warp yields 256 contiguous bytes per output plane, stored as full sectors straight
 //     into the caller-order row (the sort permutation costs nothing on output);
-//   * each lane evaluates TPL = 2 times per satellite (l and l + 32 of the warp's 64).
+//   * each lane evaluates PB_TPL times per satellite: 1 (default: a warp = 32 consecutive times, a
+//     CTA = 32 satellites x 128 times) or 2 (l and l + 32 of the warp's 64; measured equal on
+//     long grids and 3.6 % slower on 1440 times, whose last half-filled 64-group it wastes).
 // FP64 pipe bound; no tensor cores (not a contraction).
 #include "../../include/perturb_gpu.h"
 #include "batch_internal.h"
@@ -38,7 +40,10 @@ namespace {
 #endif
 constexpr int kWarps = PB_WARPS;               // warps per CTA
 constexpr int kThreads = kWarps * 32;
-constexpr int kTpl = 2;                        // times per lane
+#ifndef PB_TPL
+#define PB_TPL 1
+#endif
+constexpr int kTpl = PB_TPL;                   // times per lane (1 or 2)
 constexpr int kTimeTile = kThreads * kTpl;     // times per CTA
 
 template <int CLS>
@@ -277,14 +282,14 @@ sgp4_prop_kernel(const PropParams p) {
     }
     __syncthreads();
 
-    // Lane l of warp w owns times w*64 + l and w*64 + 32 + l of the tile: each of the two
-    // evaluations of a warp covers 32 CONSECUTIVE times, so its stores are 256 contiguous
-    // bytes per plane (full sectors) issued right after the evaluation.
+    // Lane l of warp w owns time w*32 + l of the tile (with PB_TPL = 2: w*64 + l and
+    // w*64 + 32 + l): every evaluation of a warp covers 32 CONSECUTIVE times, so its stores are
+    // 256 contiguous bytes per plane (full sectors) issued right after the evaluation.
     const int i0 = warp * (32 * kTpl) + lane;
     if (k_base + warp * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
-    // (Skipping the second group of 32 times when only it lies beyond the grid -- 1440 = 22 x 64
-    // + 32 -- was measured: a data-dependent trip count makes ptxas treat the body as divergent,
-    // +1.4 % instructions per evaluation for 2.2 % fewer evaluations, and slower overall.)
+    // (With PB_TPL = 2, skipping the second group of 32 times when only it lies beyond the grid
+    // was measured: a data-dependent trip count makes ptxas treat the body as divergent, +1.4 %
+    // instructions per evaluation; one time per lane avoids the question.)
     double ta[kTpl], tb[kTpl];
 #pragma unroll
     for (int j = 0; j < kTpl; ++j) {
@@ -314,11 +319,11 @@ sgp4_prop_kernel(const PropParams p) {
         LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
                            __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
 
-        // The two evaluations share ONE copy of the code (a rolled loop): the body is ~15 KB
+        // With PB_TPL = 2 the two evaluations share ONE copy of the code (a rolled loop): the body is ~15 KB
         // of SASS and the instruction cache is 32 KB.
 #pragma unroll 1
         for (int j = 0; j < kTpl; ++j) {
-            const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[1], (j == 0) ? tb[0] : tb[1],
+            const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[kTpl - 1], (j == 0) ? tb[0] : tb[kTpl - 1],
                                        k(PF_JD0), k(PF_JDF0));
             double r[6];
             Sgp4Side side;
@@ -358,11 +363,11 @@ sgp4_prop_kernel(const PropParams p) {
                     // one perturb::StateVector per lane: 64 contiguous bytes, four 16-byte
                     // stores; a warp covers 2 KB of the satellite's row
                     const bool written = (cd == 0) || (cd == 6);
-                    const double tj = (j == 0) ? ta[0] : ta[1];
+                    const double tj = (j == 0) ? ta[0] : ta[kTpl - 1];
                     double2 e;
                     if (p.use_jd) {
                         e.x = tj;  // sv.epoch = jd, perturb.cpp:240
-                        e.y = (j == 0) ? tb[0] : tb[1];
+                        e.y = (j == 0) ? tb[0] : tb[kTpl - 1];
                     } else {
                         e.x = k(PF_JD0);  // epoch() + mins / 1440, perturb.cpp:229 and :85-89
                         e.y = __dadd_rn(k(PF_JDF0), __ddiv_rn(tj, 1440.0));
@@ -388,7 +393,7 @@ sgp4_prop_kernel(const PropParams p) {
             }
         }
         if (MODE == kModeSummary) {
-            // Warp reduction over the 64 times of this satellite, then one partial record. The
+            // Warp reduction over this warp's times of the satellite, then one partial record. The
             // radii are non-negative doubles, which order like their bit patterns, so min / max
             // with "ties to the lowest time index" are three 32-bit warp reductions each (high
             // word, low word among the lanes that match, index among those that match both)
@@ -563,7 +568,7 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     launch_class<PB_CLS_NEAR_FULL>(l, p, stream, launches);
     launch_class<PB_CLS_NEAR_SIMP>(l, p, stream, launches);
     if (l.summary_partials != nullptr && l.summary_out != nullptr && l.n > 0) {
-        // every (satellite, chunk) partial with chunk * 64 < m has been written by exactly one
+        // every (satellite, chunk) partial with chunk * 32 * kTpl < m has been written by exactly one
         // warp of exactly one class launch; all of them were joined back into `stream`
         const int used = static_cast<int>((static_cast<size_t>(l.m) + 32 * kTpl - 1) / (32 * kTpl));
         summary_reduce_kernel<<<static_cast<unsigned>((l.n + 127) / 128), 128, 0, stream>>>(
