@@ -24,16 +24,17 @@ namespace {
 
 // Resident CTAs per SM the register allocation is capped for (measured on B200, sweeps in
 // profiles/): the near-Earth bodies need 64-70 registers and do best at 7 CTAs (28 warps/SM;
-// 8 is 1.5 % slower), the deep-space bodies at 5 (<= 102 registers; the 12 h-resonant one
-// spills 20 bytes there and is still faster than at 4).
+// 8 is within 0.5 %), the deep-space bodies at 6 (80 registers: the non-resonant and 24 h
+// bodies fit, the 12 h-resonant one spills 60 bytes and is still 1.3 % faster than at 5 CTAs
+// with 96 registers; 7 CTAs is level).
 #ifndef PB_MIN_BLOCKS_NEAR
 #define PB_MIN_BLOCKS_NEAR 7
 #endif
 #ifndef PB_MIN_BLOCKS_DEEP
-#define PB_MIN_BLOCKS_DEEP 5
+#define PB_MIN_BLOCKS_DEEP 6
 #endif
 #ifndef PB_MIN_BLOCKS_R2
-#define PB_MIN_BLOCKS_R2 5
+#define PB_MIN_BLOCKS_R2 6
 #endif
 #ifndef PB_WARPS
 #define PB_WARPS 4
