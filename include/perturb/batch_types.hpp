@@ -11,7 +11,8 @@
  *   perturb::GravModel       include/perturb/perturb.hpp:69-73
  *   perturb::Vec3            include/perturb/perturb.hpp:35
  *   perturb::DateTime        include/perturb/perturb.hpp:95-102
- *   perturb::JulianDate      include/perturb/perturb.hpp:117-191 (jd, jd_frac; DateTime ctor, operator-)
+ *   perturb::JulianDate      include/perturb/perturb.hpp:117-191 (the whole interface: conversions
+ *                            both ways, normalize, offsets, ordering)
  *   perturb::StateVector     include/perturb/perturb.hpp:198-205
  *   perturb::TwoLineElement  include/perturb/tle.hpp:65-91       (numeric members the path reads)
  */
@@ -76,13 +77,85 @@ struct JulianDate {
     explicit JulianDate(double _jd) : jd(_jd), jd_frac(0) {}
     explicit JulianDate(double _jd, double _jd_frac) : jd(_jd), jd_frac(_jd_frac) {}
 
+    /// Same time point as a calendar date (perturb.cpp:54-58): the arithmetic of
+    /// sgp4::invjday_SGP4 and sgp4::days2mdhms_SGP4 (sgp4.cpp:3232-3279, 3161-3192).
+    DateTime to_datetime() const {
+        double day_no = jd, part = jd_frac;
+        if (std::fabs(part) >= 1.0) {  // whole days hiding in the fraction
+            day_no = day_no + std::floor(part);
+            part = part - std::floor(part);
+        }
+        const double off = day_no - std::floor(day_no) - 0.5;  // fraction hiding in the day
+        if (std::fabs(off) > 0.00000001) {
+            day_no = day_no - off;
+            part = part + off;
+        }
+        const double since1900 = day_no - 2415019.5;
+        DateTime t = DateTime();
+        t.year = 1900 + static_cast<int>(std::floor(since1900 / 365.25));
+        int leaps = static_cast<int>(std::floor((t.year - 1901) * 0.25));
+        double days = std::floor(since1900 - ((t.year - 1900) * 365.0 + leaps));
+        if (days + part < 1.0) {  // the very beginning of a year belongs to the year before
+            t.year = t.year - 1;
+            leaps = static_cast<int>(std::floor((t.year - 1901) * 0.25));
+            days = std::floor(since1900 - ((t.year - 1900) * 365.0 + leaps));
+        }
+        // day of year (with fraction) -> month, day, hour, minute, second
+        const double doy = days + part;
+        const int whole = static_cast<int>(std::floor(doy));
+        const int feb = (t.year % 4) == 0 ? 29 : 28;
+        const int len[12] = {31, feb, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+        int m = 0, before = 0;
+        while (whole > before + len[m] && m < 11) {
+            before += len[m];
+            ++m;
+        }
+        t.month = m + 1;
+        t.day = whole - before;
+        double rest = (doy - whole) * 24.0;
+        t.hour = static_cast<int>(std::floor(rest));
+        rest = (rest - t.hour) * 60.0;
+        t.min = static_cast<int>(std::floor(rest));
+        t.sec = (rest - t.min) * 60.0;
+        return t;
+    }
+
+    /// Whole days in `jd` (at midnight, x.5), a [0, 1) offset in `jd_frac` (perturb.cpp:60-73).
+    void normalize() {
+        const double frac_days = jd - std::floor(jd) - 0.5;
+        if (std::fabs(frac_days) > 1e-12) {
+            jd -= frac_days;
+            jd_frac += frac_days;
+        }
+        if (std::fabs(jd_frac) >= 1.0) {
+            const double whole_days = std::floor(jd_frac);
+            jd += whole_days;
+            jd_frac -= whole_days;
+        }
+    }
+    JulianDate normalized() const {
+        JulianDate other = *this;
+        other.normalize();
+        return other;
+    }
+
     /// Difference in days; the grouping preserves precision (perturb.cpp:80-83).
     double operator-(const JulianDate &rhs) const {
         return (this->jd - rhs.jd) + (this->jd_frac - rhs.jd_frac);
     }
+    /// Offset by days, added to `jd_frac` only: not normalized (perturb.cpp:85-101).
     JulianDate operator+(const double &delta_jd) const {
         return JulianDate(jd, jd_frac + delta_jd);
     }
+    JulianDate &operator+=(const double &delta_jd) { return *this = *this + delta_jd; }
+    JulianDate operator-(const double &delta_jd) const { return *this + (-delta_jd); }
+    JulianDate &operator-=(const double &delta_jd) { return *this = *this - delta_jd; }
+
+    /// Chronological order through the precise difference (perturb.cpp:103-117).
+    bool operator<(const JulianDate &rhs) const { return (*this - rhs) < 0; }
+    bool operator>(const JulianDate &rhs) const { return (*this - rhs) > 0; }
+    bool operator<=(const JulianDate &rhs) const { return (*this - rhs) <= 0; }
+    bool operator>=(const JulianDate &rhs) const { return (*this - rhs) >= 0; }
 };
 
 struct StateVector {

@@ -139,3 +139,39 @@ def test_cpp_sharded_batch_equals_the_unsharded_one(tmp_path, shards):
     assert "device_gather_equal 1 device_gather_codes_equal 1 status 0" in out, out
     cuts = [int(x) for x in out.splitlines()[0].split("cuts")[1].split()]
     assert len(cuts) == shards and cuts[-1] == 3000
+
+
+JULIAN_SRC = os.path.join(ROOT, "tests", "cpp", "julian_dates.cpp")
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
+def test_julian_date_and_datetime_equal_the_reference(tmp_path):
+    """The stand-alone perturb::JulianDate / DateTime (include/perturb/batch_types.hpp) against
+    the reference's (perturb.cpp:40-117 over jday_SGP4 / invjday_SGP4): conversions both ways
+    for 24 776 time points of 1901-2099, normalisation, offsets and ordering print the same
+    text, digit for digit, as the same program built on the reference's headers and sources
+    (golden hash made by tests/golden/make_julian_golden.sh; compared live when the reference
+    tree is present)."""
+    import hashlib
+    exe = str(tmp_path / "julian_ours")
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror",
+                           "-I" + os.path.join(ROOT, "include"), JULIAN_SRC, "-o", exe])
+    ours = subprocess.run([exe], capture_output=True, check=True).stdout
+    want_hash, want_lines = open(os.path.join(ROOT, "tests", "golden", "julian_dates.sha256")).read().split()
+    assert len(ours.splitlines()) == int(want_lines)
+    assert hashlib.sha256(ours).hexdigest() == want_hash
+    if os.path.isdir(REF_INCLUDE):
+        ref_exe = str(tmp_path / "julian_ref")
+        src = "/root/reference/src/"
+        subprocess.check_call(["g++", "-std=c++11", "-w", "-DPERTURB_BATCH_USE_PERTURB_HPP",
+                               "-I" + REF_INCLUDE, "-I" + os.path.join(ROOT, "include"), JULIAN_SRC,
+                               src + "perturb.cpp", src + "sgp4.cpp", src + "tle.cpp", "-o", ref_exe])
+        ref = subprocess.run([ref_exe], capture_output=True, check=True).stdout
+        assert ours == ref
+    # the reference's own round-trip bar (tests/test_perturb.cpp:109-129): jd exact, frac to 1e-12
+    for ln in ours.decode().splitlines()[:4776:97]:
+        f = ln.split()
+        jd, fr = float(f[1]), float(f[2])
+        y, mo, d, h, mi, s = int(f[4]), int(f[5]), int(f[6]), int(f[7]), int(f[8]), float(f[9])
+        jd2 = 367.0 * y - np.floor(7 * (y + np.floor((mo + 9) / 12.0)) * 0.25) + np.floor(275 * mo / 9.0) + d + 1721013.5
+        assert jd2 == jd and abs((s + mi * 60.0 + h * 3600.0) / 86400.0 - fr) < 1e-12
