@@ -14,7 +14,8 @@
  *   perturb::JulianDate      include/perturb/perturb.hpp:117-191 (the whole interface: conversions
  *                            both ways, normalize, offsets, ordering)
  *   perturb::StateVector     include/perturb/perturb.hpp:198-205
- *   perturb::TwoLineElement  include/perturb/tle.hpp:65-91       (numeric members the path reads)
+ *   perturb::TwoLineElement  include/perturb/tle.hpp:65-91       (every member; parse() over the
+ *                            library's exact fixed-column reader), TLEParseError, TLE_LINE_LEN
  */
 #ifndef PERTURB_BATCH_TYPES_HPP
 #define PERTURB_BATCH_TYPES_HPP
@@ -28,6 +29,10 @@
 #include <array>
 #include <cmath>
 #include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../perturb_gpu.h"
 
 namespace perturb {
 
@@ -164,21 +169,91 @@ struct StateVector {
     Vec3 velocity;  ///< TEME [km/s]
 };
 
-/// Numeric members of a parsed TLE, TLE units (deg, rev/day).
+/// Number of characters of one TLE line (include/perturb/tle.hpp:33).
+constexpr std::size_t TLE_LINE_LEN = 69;
+
+/// Outcome of `TwoLineElement::parse`, in checking order (include/perturb/tle.hpp:45-51).
+enum class TLEParseError {
+    NONE,
+    SHOULD_BE_SPACE,
+    INVALID_FORMAT,
+    INVALID_VALUE,
+    CHECKSUM_MISMATCH,
+};
+
+/// A parsed TLE record, TLE units (deg, rev/day): member for member the reference's
+/// (include/perturb/tle.hpp:65-91). The batch reads the numeric ones.
 struct TwoLineElement {
+    // Line 1
     char catalog_number[6];
     char classification;
+    unsigned int launch_year;
+    unsigned int launch_number;
+    char launch_piece[4];
     unsigned int epoch_year;
     double epoch_day_of_year;
     double n_dot;
     double n_ddot;
     double b_star;
+    unsigned char ephemeris_type;
+    unsigned int element_set_number;
+    unsigned char line_1_checksum;
+    // Line 2
     double inclination;
     double raan;
     double eccentricity;
     double arg_of_perigee;
     double mean_anomaly;
     double mean_motion;
+    unsigned long revolution_number;
+    unsigned char line_2_checksum;
+
+    /// `TwoLineElement::parse` (src/tle.cpp:41-173) over the library's restatement of the
+    /// reference's sscanf directives (`perturb_gpu_parse_tle`): same values bit for bit, same
+    /// error in the same checking order, including the lines the reference rejects because a
+    /// blank field shifts its tokens. Lines must hold TLE_LINE_LEN characters.
+    TLEParseError parse(const char *line_1, const char *line_2) {
+        perturb_gpu_tle num;
+        perturb_gpu_tle_ident id;
+        const int status = perturb_gpu_parse_tle(line_1, line_2, &num, &id);
+        if (status < 0) {
+            return TLEParseError::INVALID_FORMAT;
+        }
+        if (status == 0 || status >= 3) {  // every field was read
+            for (int i = 0; i < 6; ++i) {
+                catalog_number[i] = id.catalog_number[i];
+            }
+            classification = id.classification;
+            launch_year = id.launch_year;
+            launch_number = id.launch_number;
+            for (int i = 0; i < 4; ++i) {
+                launch_piece[i] = id.launch_piece[i];
+            }
+            ephemeris_type = id.ephemeris_type;
+            element_set_number = id.element_set_number;
+            line_1_checksum = id.line_1_checksum;
+            revolution_number = id.revolution_number;
+            line_2_checksum = id.line_2_checksum;
+            epoch_year = static_cast<unsigned int>(num.epoch_year);
+            epoch_day_of_year = num.epoch_day_of_year;
+            n_dot = num.n_dot;
+            n_ddot = num.n_ddot;
+            b_star = num.b_star;
+            inclination = num.inclination;
+            raan = num.raan;
+            eccentricity = num.eccentricity;
+            arg_of_perigee = num.arg_of_perigee;
+            mean_anomaly = num.mean_anomaly;
+            mean_motion = num.mean_motion;
+        }
+        return static_cast<TLEParseError>(status);
+    }
+    TLEParseError parse(const std::string &line_1, const std::string &line_2) {
+        if (line_1.length() < TLE_LINE_LEN || line_2.length() < TLE_LINE_LEN) {
+            return TLEParseError::INVALID_FORMAT;
+        }
+        return this->parse(line_1.c_str(), line_2.c_str());
+    }
 };
 
 }  // namespace perturb

@@ -283,6 +283,30 @@ const char *perturb_gpu_strerror(void);
 int perturb_gpu_parse_tles(const char *lines1, const char *lines2, size_t line_stride, size_t n,
                            int flavor, perturb_gpu_tle *out, int32_t *status);
 
+/* The members of perturb::TwoLineElement (include/perturb/tle.hpp:65-91) that are not numbers
+ * the propagator reads. */
+typedef struct perturb_gpu_tle_ident {
+    char catalog_number[6];
+    char classification;
+    unsigned int launch_year;
+    unsigned int launch_number;
+    char launch_piece[4];
+    unsigned char ephemeris_type;
+    unsigned int element_set_number;
+    unsigned char line_1_checksum;
+    unsigned long revolution_number;
+    unsigned char line_2_checksum;
+} perturb_gpu_tle_ident;
+
+/* One `TwoLineElement::parse(line_1, line_2)` (src/tle.cpp:41-173): returns the
+ * perturb::TLEParseError value (0 NONE .. 4 CHECKSUM_MISMATCH, same checking order), or a
+ * negative library status for null arguments. The reference's sscanf directives are restated
+ * token for token, so blank or misplaced fields are rejected (or accepted) exactly as there.
+ * `numbers` / `ident` are written when every field could be read (results 0, 3 and 4);
+ * `ident` may be NULL. Both lines must hold 69 characters. */
+int perturb_gpu_parse_tle(const char *line_1, const char *line_2, perturb_gpu_tle *numbers,
+                          perturb_gpu_tle_ident *ident);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ EXPORTS = (
     "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_states perturb_gpu_propagate_elements perturb_gpu_propagate_summary perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_device_count perturb_gpu_host_alloc perturb_gpu_host_free perturb_gpu_device_alloc perturb_gpu_device_free perturb_gpu_copy perturb_gpu_size "
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
-    "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles "
+    "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles perturb_gpu_parse_tle "
     "perturb_gpu_measure_fp64_peak perturb_gpu_math_probe "
     "perturb_synth_catalog perturb_synth_time_grid"
 ).split()

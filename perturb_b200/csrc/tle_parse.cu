@@ -73,3 +73,18 @@ extern "C" int perturb_gpu_parse_tles(const char *lines1, const char *lines2,
     }
     return PERTURB_GPU_OK;
 }
+
+extern "C" int perturb_gpu_parse_tle(const char *line_1, const char *line_2,
+                                     perturb_gpu_tle *numbers, perturb_gpu_tle_ident *ident) {
+    if (line_1 == nullptr || line_2 == nullptr || numbers == nullptr) return PERTURB_GPU_ERR_ARG;
+    if (pb::tle::has_nul(line_1) || pb::tle::has_nul(line_2)) return 2;  // INVALID_FORMAT
+    static const pb::tle::Pow10Table pw = host_pow_table();
+    perturb_gpu_tle t;
+    perturb_gpu_tle_ident id;
+    const int st = pb::tle::parse_perturb(line_1, line_2, pw, t, &id);
+    if (st == 0 || st >= 3) {
+        *numbers = t;
+        if (ident != nullptr) *ident = id;
+    }
+    return st;
+}

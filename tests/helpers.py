@@ -128,3 +128,41 @@ def make_tle(satnum, epoch_year2, epoch_day, inc_deg, raan_deg, ecc, argp_deg, m
         satnum, inc_deg, raan_deg, int(round(ecc * 1e7)), argp_deg, ma_deg, n_revday, 1)
     assert len(l1) == 68 and len(l2) == 68, (len(l1), len(l2))
     return l1 + tle_checksum(l1), l2 + tle_checksum(l2)
+
+
+def tle_parser_feed():
+    """Deterministic text fed to tests/cpp/tle_members.cpp: the verification catalogue, the ISS
+    example and synthetic TLEs as they are, then 30 000 corrupted pairs (characters replaced,
+    runs blanked, tails shifted) over the alphabet a damaged TLE plausibly holds."""
+    import random
+    import perturb_b200 as pb
+    rnd = random.Random(7)
+    here = os.path.dirname(os.path.abspath(__file__))
+    lines = [ln.rstrip("\n") for ln in open(os.path.join(here, "golden", "SGP4-VER.TLE"))
+             if ln[:1] in "12"]
+    lines += ["1 25544U 98067A   22071.78032407  .00021395  00000-0  39008-3 0  9996",
+              "2 25544  51.6424  94.0370 0004047 256.5103  89.8846 15.49386383330227"]
+    for cfg in (2, 3, 4, 5):
+        b1, b2 = pb.synth_catalog(cfg, 500)
+        for a, b in zip(pb.block_to_lines(b1, 500), pb.block_to_lines(b2, 500)):
+            lines += [a, b]
+    pairs = [(lines[i][:69].ljust(69), lines[i + 1][:69].ljust(69)) for i in range(0, len(lines), 2)]
+    alpha = " 0123456789.+-UAZ"
+    out = [x for p in pairs for x in p]
+    for _ in range(30000):
+        a, b = rnd.choice(pairs)
+        a, b = list(a), list(b)
+        for _ in range(rnd.choice([1, 1, 1, 2, 3])):
+            L = a if rnd.random() < 0.5 else b
+            pos = rnd.randrange(69)
+            mode = rnd.random()
+            if mode < 0.6:
+                L[pos] = rnd.choice(alpha)
+            elif mode < 0.8:
+                for j in range(pos, min(69, pos + rnd.randint(1, 6))):
+                    L[j] = " "
+            else:
+                L[pos + 1:] = L[pos:-1]
+                L[pos] = rnd.choice(alpha)
+        out += ["".join(a), "".join(b)]
+    return ("\n".join(out) + "\n").encode()
