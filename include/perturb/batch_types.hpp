@@ -169,6 +169,24 @@ struct StateVector {
     Vec3 velocity;  ///< TEME [km/s]
 };
 
+/// Classical Keplerian elements, member for member the reference's
+/// (include/perturb/perturb.hpp:211-222; [km] and [rad]). The batch computes them for whole
+/// propagate results on the device (`SatelliteBatch::classical_elements_soa`, eleven planes
+/// in this member order); there is no per-state host constructor here -- no CPU path.
+struct ClassicalOrbitalElements {
+    double semilatus_rectum;
+    double semimajor_axis;
+    double eccentricity;
+    double inclination;
+    double raan;
+    double arg_of_perigee;
+    double true_anomaly;
+    double mean_anomaly;
+    double arg_of_latitude;
+    double true_longitude;
+    double longitude_of_periapsis;
+};
+
 /// Number of characters of one TLE line (include/perturb/tle.hpp:33).
 constexpr std::size_t TLE_LINE_LEN = 69;
 

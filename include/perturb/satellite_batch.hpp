@@ -187,6 +187,21 @@ public:
         return status_;
     }
 
+    /// Batched `ClassicalOrbitalElements(sv, grav_model)` (perturb.cpp:119-131) over the planes
+    /// a `propagate_soa` call wrote into DEVICE memory: eleven planes in the member order of
+    /// `perturb::ClassicalOrbitalElements`, coe[e * coe_plane_stride + i * row_stride + k]
+    /// (device memory; see perturb_gpu_rv2coe for sentinels and NaN conventions).
+    static int classical_elements_soa(
+        const double *posvel, std::size_t n, std::size_t m, std::size_t row_stride,
+        std::size_t plane_stride, GravModel grav_model, double *coe,
+        std::size_t coe_plane_stride, void *stream
+    ) {
+        return perturb_gpu_rv2coe(
+            posvel, n, m, row_stride, plane_stride, grav_code(grav_model), coe, coe_plane_stride,
+            stream
+        );
+    }
+
     perturb_gpu_batch *handle() { return handle_; }
 
 private:
