@@ -163,6 +163,7 @@ struct perturb_gpu_batch {
     int *d_res_k0, *d_res_cnt;
     double *d_res_range;
     int res_cap;
+    unsigned long long peers_enabled;  // bit d: this device already has peer access to device d
     cudaStream_t aux[PB_CLS_COUNT];  // forked streams, one per orbit class
     cudaEvent_t ev_fork, ev_join[PB_CLS_COUNT];
     int last_launches;
@@ -184,6 +185,7 @@ struct perturb_gpu_batch {
         d_res_k0 = d_res_cnt = nullptr;
         d_res_range = nullptr;
         res_cap = 0;
+        peers_enabled = 0;
         for (int b = 0; b < 2; ++b) {
             d_stage[b] = nullptr;
             d_stage_err[b] = nullptr;
@@ -491,6 +493,15 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
     }
 }
 
+// ensure_peer_access once per (batch, owner device)
+int peer_ready(perturb_gpu_batch *b, int owner) {
+    if (owner < 0 || owner == b->device) return PERTURB_GPU_OK;
+    if (owner < 64 && ((b->peers_enabled >> owner) & 1ULL)) return PERTURB_GPU_OK;
+    const int st = ensure_peer_access(b->device, owner);
+    if (st == PERTURB_GPU_OK && owner < 64) b->peers_enabled |= 1ULL << owner;
+    return st;
+}
+
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
                    size_t m, double *posvel, int32_t *err, size_t row_stride,
                    size_t plane_stride, void *stream_arg, double *elements = nullptr,
@@ -559,7 +570,7 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         // device-resident gather: the buffers may belong to another GPU of this process
         for (const void *q : {static_cast<const void *>(posvel), static_cast<const void *>(err),
                               static_cast<const void *>(elements)}) {
-            const int st = ensure_peer_access(b->device, pointer_device(q));
+            const int st = peer_ready(b, pointer_device(q));
             if (st != PERTURB_GPU_OK) return st;
         }
         l.ta = d_ta;
@@ -776,7 +787,7 @@ int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const 
     perturb_gpu_summary *folded = partials + b->n * chunks;
     const bool out_dev = is_device_pointer(out);
     if (out_dev) {
-        const int st = ensure_peer_access(b->device, pointer_device(out));
+        const int st = peer_ready(b, pointer_device(out));
         if (st != PERTURB_GPU_OK) return st;
     }
 
