@@ -207,3 +207,21 @@ def test_twolineelement_parse_equals_the_reference_member_for_member(tmp_path):
                                src + "perturb.cpp", src + "sgp4.cpp", src + "tle.cpp", "-o", ref_exe])
         ref = subprocess.run([ref_exe], input=feed, capture_output=True, check=True).stdout
         assert ours == ref
+
+
+# the reference's developer preset (CMakePresets.json:57-62 "flags-unix"), as errors
+REFERENCE_WARNING_FLAGS = (
+    "-Wall -Wextra -Wpedantic -Wconversion -Wsign-conversion -Wcast-qual -Wcast-align -Wshadow "
+    "-Wformat=2 -Wformat-overflow -Wformat-truncation -Wundef -Wdouble-promotion "
+    "-Wstrict-overflow=5 -Wno-maybe-uninitialized -Wno-unused-result").split()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
+@pytest.mark.parametrize("src", ["iss_example.cpp", "sharded_example.cpp", "julian_dates.cpp",
+                                 "tle_members.cpp"])
+def test_headers_are_clean_under_the_reference_developer_flags(src):
+    """The drop-in headers compile as C++11 without a single warning under the warning set the
+    reference builds itself with in developer mode."""
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-fsyntax-only", "-Werror",
+                           *REFERENCE_WARNING_FLAGS, "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", src)])
