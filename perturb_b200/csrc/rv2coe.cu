@@ -282,7 +282,8 @@ __device__ __forceinline__ bool rv2coe_fast(const double r[3], const double v[3]
     // (|hk| = cos 1e-8 is 1 - 5e-17: anything below 1 - 1e-12 is safely inclined)
     const bool regular = (hh > 1.0e-12) && (nn > 1.0e-12) && (ecc > 1.0e-6) && (ecc < 0.999999) &&
                          (fabs(hk) < 0.999999999999) && (fabs(sme) > 1.0e-6) && (rr > 1.0e-12);
-    if (!regular) return false;
+    // (no early return: with one, everything below counts as divergent code and loses the
+    // uniform datapath for its constants; an irregular state just computes garbage here)
 
     const double incl = acos_fast(hk);
     double omega = acos_fast(clamp1(__dmul_rn(-h[1], inv_n)));
@@ -318,7 +319,7 @@ __device__ __forceinline__ bool rv2coe_fast(const double r[3], const double v[3]
     out[8] = kUndefined;
     out[9] = kUndefined;
     out[10] = kUndefined;
-    return true;
+    return regular;
 }
 
 // The general routine as a real call that stores its own results: it runs for a vanishing share
@@ -337,10 +338,12 @@ __global__ void __launch_bounds__(256, 4)
 rv2coe_kernel(const double *__restrict__ posvel, size_t n, size_t m, size_t row_stride,
               size_t plane_stride, double mus, double inv_mus, double *__restrict__ coe,
               size_t coe_plane_stride) {
-    const size_t i = static_cast<size_t>(blockIdx.z) * 65535u + blockIdx.y;
-    const size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (k >= m || i >= n) return;
-    const size_t at = i * row_stride + k;  // lanes = consecutive times: coalesced planes
+    const size_t i = static_cast<size_t>(blockIdx.z) * 65535u + blockIdx.y;  // < n by the grid
+    const size_t k_own = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // lanes past the end of the row redo its last state and store nothing: no early return, so
+    // the arithmetic below stays warp-uniform code
+    const bool in_row = k_own < m;
+    const size_t at = i * row_stride + (in_row ? k_own : m - 1);  // lanes = consecutive times
     double r[3], v[3], out[11];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -348,18 +351,16 @@ rv2coe_kernel(const double *__restrict__ posvel, size_t n, size_t m, size_t row_
         v[c] = posvel[(c + 3) * plane_stride + at];
     }
     const bool have = !(isnan(r[0]) || isnan(v[0]));  // codes 1-4 carry no state
-    if (have) {
-        if (!rv2coe_fast(r, v, mus, inv_mus, out)) {
+    const bool fast = rv2coe_fast(r, v, mus, inv_mus, out);
+    if (in_row) {
+        if (have && !fast) {
             rv2coe_general_store(r[0], r[1], r[2], v[0], v[1], v[2], mus, coe + at, coe_plane_stride);
-            return;
+        } else {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+            for (int c = 0; c < 11; ++c) coe[c * coe_plane_stride + at] = have ? out[c] : nan;
         }
-    } else {
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-        for (int c = 0; c < 11; ++c) out[c] = nan;
     }
-#pragma unroll
-    for (int c = 0; c < 11; ++c) coe[c * coe_plane_stride + at] = out[c];
 }
 
 bool on_device(const void *p) {
