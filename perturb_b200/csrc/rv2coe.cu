@@ -338,12 +338,14 @@ __global__ void __launch_bounds__(256, 4)
 rv2coe_kernel(const double *__restrict__ posvel, size_t n, size_t m, size_t row_stride,
               size_t plane_stride, double mus, double inv_mus, double *__restrict__ coe,
               size_t coe_plane_stride) {
-    const size_t i = static_cast<size_t>(blockIdx.z) * 65535u + blockIdx.y;  // < n by the grid
+    const size_t i_own = static_cast<size_t>(blockIdx.z) * 65535u + blockIdx.y;
     const size_t k_own = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    // lanes past the end of the row redo its last state and store nothing: no early return, so
-    // the arithmetic below stays warp-uniform code
-    const bool in_row = k_own < m;
-    const size_t at = i * row_stride + (in_row ? k_own : m - 1);  // lanes = consecutive times
+    // lanes past the end of the row (or rows past the last satellite, in the last grid slab)
+    // redo a state that exists and store nothing: no early return, so the arithmetic below
+    // stays warp-uniform code
+    const bool in_row = (k_own < m) && (i_own < n);
+    const size_t i = i_own < n ? i_own : n - 1;
+    const size_t at = i * row_stride + (k_own < m ? k_own : m - 1);  // lanes = consecutive times
     double r[3], v[3], out[11];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -391,10 +393,20 @@ extern "C" int perturb_gpu_rv2coe(const double *posvel, size_t n, size_t m, size
     }
     if (n == 0 || m == 0) return PERTURB_GPU_OK;
     if (!on_device(posvel) || !on_device(coe)) return PERTURB_GPU_ERR_ARG;  // device buffers only
-    const dim3 grid(static_cast<unsigned>((m + 255) / 256),
+    // CTA width that wastes the fewest lanes at the end of a row (1440 times: 9 x 160, none)
+    unsigned threads = 256;
+    size_t waste = ((m + 255) / 256) * 256 - m;
+    for (unsigned t = 224; t >= 128; t -= 32) {
+        const size_t w = ((m + t - 1) / t) * t - m;
+        if (w < waste) {
+            waste = w;
+            threads = t;
+        }
+    }
+    const dim3 grid(static_cast<unsigned>((m + threads - 1) / threads),
                     static_cast<unsigned>(n < 65535 ? n : 65535),
                     static_cast<unsigned>((n + 65534) / 65535));
-    rv2coe_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    rv2coe_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         posvel, n, m, row_stride, plane_stride, mus, 1.0 / mus, coe, coe_plane_stride);
     return cudaGetLastError() == cudaSuccess ? PERTURB_GPU_OK : PERTURB_GPU_ERR_CUDA;
 }

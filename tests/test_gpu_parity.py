@@ -493,6 +493,35 @@ def test_classical_elements_batch():
 COE_J = pb.COE_NAMES
 
 
+def test_classical_elements_beyond_one_grid_slab_and_row_tails():
+    """More satellites than one grid slab (65 535) and a row length that is no multiple of any
+    CTA width: rows past the slab boundary equal a separate call on just those rows bit for
+    bit, and nothing is written outside [n][m] (sentinel margins)."""
+    import torch
+    n, m, row = 70001, 7, 10
+    b1, b2 = pb.synth_catalog(5, n)
+    b = pb.SatelliteBatch.from_text(b1, b2, pb.WGS72, "i", device=0, n=n)
+    mins = np.linspace(0.0, 90.0, m)
+    dev = torch.device("cuda", 0)
+    pv = torch.full((6, n, row), 7.0, dtype=torch.float64, device=dev)
+    err = torch.zeros((n, row), dtype=torch.int32, device=dev)
+    b.propagate_from_epoch(torch.tensor(mins, device=dev), pv[:, :, :m], err[:, :m])
+    guard = 3
+    coe = torch.full((11, n + guard, row), -5.0, dtype=torch.float64, device=dev)
+    L = pb.capi.lib()
+    pb.capi.check(L.perturb_gpu_rv2coe(pv.data_ptr(), n, m, row, n * row, int(pb.WGS72),
+                                       coe.data_ptr(), (n + guard) * row, None), "rv2coe")
+    torch.cuda.synchronize(dev)
+    got = coe.cpu().numpy()
+    assert (got[:, n:, :] == -5.0).all() and (got[:, :, m:] == -5.0).all()  # margins untouched
+    assert np.isfinite(got[:, :n, :m]).all()
+    lo = 65500
+    part = pb.classical_elements(pv[:, lo:, :m]).cpu().numpy()
+    assert np.array_equal(got[:, lo:n, :m], part)
+    a = got[1, :n, :m]
+    assert (a > 6500.0).all() and (a < 7500.0).all()  # mega-constellation shells
+
+
 # ---- N1: TLE text parsed on the device ------------------------------------------------------
 @pytest.mark.parametrize("flavor", [0, 1])
 def test_device_tle_parser_equals_host_parser(flavor):
