@@ -449,6 +449,114 @@ sgp4_prop_kernel(const PropParams p) {
     }
 }
 
+// Kernel 2 for SHORT time grids (a whole catalogue at one epoch, or a handful): with lanes =
+// times a warp of the kernel above would have m of its 32 lanes busy. Here lanes are 32
+// class-sorted SATELLITES of one tile and every lane walks the few times; the constants come
+// straight from the field-major layout (one coalesced 256 B row per field, L1 resident across
+// the times). The evaluation is the same code on the same inputs, so the result of a
+// (satellite, time) pair is bit-identical to the other kernel's (tested).
+#ifndef PB_SHORT_GRID
+#define PB_SHORT_GRID 16
+#endif
+constexpr int kShortGrid = PB_SHORT_GRID;  // grids up to this many times take this kernel
+
+template <int CLS, int MODE>
+__global__ void __launch_bounds__(kThreads)
+sgp4_prop_short_kernel(const PropParams p, int tile_count) {
+    constexpr bool WANT_ELEMENTS = (MODE == kModeElements);
+    constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (__all_sync(0xffffffffu, tile >= tile_count)) return;
+    const size_t slot_own = static_cast<size_t>(p.tile_begin + tile) * PB_TILE_SATS + lane;
+    const int dst = p.perm[slot_own];
+    // a padding lane (only at the end of a class segment, never first in its tile) redoes the
+    // tile's first satellite and stores nothing: every lane stays active for the votes
+    const size_t slot = (dst >= 0) ? slot_own : slot_own - lane;
+    const GlobalConsts k = {p.pf + slot, p.n_pad};
+    ResNodes nodes = {nullptr, 0, 0, 0};
+    if (kResonant && p.res_nodes != nullptr) {
+        const size_t rs = slot - p.res_first_slot;
+        nodes.table = p.res_nodes;
+        nodes.k0 = p.res_k0[rs];
+        nodes.count = p.res_cnt[rs];
+        nodes.first = static_cast<int>(rs) * p.res_cap;
+    }
+    const ClassFlags no_flags = {false, false, 0};
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double jd0 = k(PF_JD0), jdf0 = k(PF_JDF0);
+    LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
+                       __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
+#pragma unroll 1
+    for (int kt = 0; kt < p.m; ++kt) {
+        const double ta = p.ta[kt], tb = p.use_jd ? p.tb[kt] : 0.0;
+        const double t = tsince_of(p.use_jd, ta, tb, jd0, jdf0);
+        double r[6];
+        Sgp4Side side;
+        const int cd = sgp4_eval<CLS, WANT_ELEMENTS, true>(
+            k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
+            (kResonant && nodes.table != nullptr) ? &nodes : nullptr);
+        if (dst < 0) continue;
+        const bool written = (cd == 0) || (cd == 6);
+        if (MODE == kModeSummary) {
+            if (cd == 0) {
+                const double rr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                if (rr < acc.r_min) { acc.r_min = rr; acc.k_min = kt; }
+                if (rr > acc.r_max) { acc.r_max = rr; acc.k_max = kt; }
+                acc.n_ok += 1;
+            } else if (acc.k_err < 0) {
+                acc.k_err = kt;
+                acc.code_err = cd;
+            }
+        } else if (MODE == kModeRecords) {
+            double2 e;
+            if (p.use_jd) {
+                e.x = ta;  // sv.epoch = jd, perturb.cpp:240
+                e.y = tb;
+            } else {
+                e.x = jd0;  // epoch() + mins / 1440, perturb.cpp:229 and :85-89
+                e.y = __dadd_rn(jdf0, __ddiv_rn(ta, 1440.0));
+            }
+            double2 *rec = reinterpret_cast<double2 *>(
+                p.states + (static_cast<size_t>(dst) * p.row_stride + kt) * 8);
+            rec[0] = e;
+            rec[1] = make_double2(written ? r[0] : nan, written ? r[1] : nan);
+            rec[2] = make_double2(written ? r[2] : nan, written ? r[3] : nan);
+            rec[3] = make_double2(written ? r[4] : nan, written ? r[5] : nan);
+            p.err[static_cast<size_t>(dst) * p.err_row_stride + kt] = cd;
+        } else {
+            double *row = p.out + static_cast<size_t>(dst) * p.row_stride + kt;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) row[c * p.plane_stride] = written ? r[c] : nan;
+            p.err[static_cast<size_t>(dst) * p.err_row_stride + kt] = cd;
+            if (WANT_ELEMENTS) {
+                const bool stored = side.stage >= 1;
+                double *el = p.elements + static_cast<size_t>(dst) * p.row_stride + kt;
+                el[0 * p.plane_stride] = stored ? side.am : nan;
+                el[1 * p.plane_stride] = stored ? side.em : nan;
+                el[2 * p.plane_stride] = stored ? side.im : nan;
+                el[3 * p.plane_stride] = stored ? side.Om : nan;
+                el[4 * p.plane_stride] = stored ? side.om : nan;
+                el[5 * p.plane_stride] = stored ? side.mm : nan;
+                el[6 * p.plane_stride] = stored ? side.nm : nan;
+            }
+        }
+    }
+    if (MODE == kModeSummary && dst >= 0) {
+        // the whole (short) grid is this lane's: chunk 0 holds the satellite's summary
+        perturb_gpu_summary out;
+        out.r_min = acc.r_min;
+        out.r_max = acc.r_max;
+        out.k_min = acc.k_min;
+        out.k_max = acc.k_max;
+        out.n_ok = acc.n_ok;
+        out.first_error = acc.code_err;
+        out.k_first_error = acc.k_err;
+        out.reserved = 0;
+        p.partials[static_cast<size_t>(dst) * p.chunks] = out;
+    }
+}
+
 // Second pass of the summary mode: one thread per satellite folds its chunk partials.
 __global__ void __launch_bounds__(128)
 summary_reduce_kernel(const perturb_gpu_summary *__restrict__ partials, int chunks, int used_chunks,
@@ -488,7 +596,18 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
         stream = l.aux[CLS];
         cudaStreamWaitEvent(stream, l.fork, 0);
     }
-    if (p.partials != nullptr) {
+    if (p.m <= kShortGrid) {
+        const unsigned sb = static_cast<unsigned>((tiles + kWarps - 1) / kWarps);
+        if (p.partials != nullptr) {
+            sgp4_prop_short_kernel<CLS, kModeSummary><<<sb, kThreads, 0, stream>>>(p, tiles);
+        } else if (p.states != nullptr) {
+            sgp4_prop_short_kernel<CLS, kModeRecords><<<sb, kThreads, 0, stream>>>(p, tiles);
+        } else if (p.elements != nullptr) {
+            sgp4_prop_short_kernel<CLS, kModeElements><<<sb, kThreads, 0, stream>>>(p, tiles);
+        } else {
+            sgp4_prop_short_kernel<CLS, kModeStates><<<sb, kThreads, 0, stream>>>(p, tiles);
+        }
+    } else if (p.partials != nullptr) {
         sgp4_prop_kernel<CLS, kModeSummary><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     } else if (p.states != nullptr) {
         sgp4_prop_kernel<CLS, kModeRecords><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);

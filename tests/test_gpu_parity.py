@@ -600,6 +600,54 @@ def test_time_chunking_and_strided_output_are_bit_invariant():
     assert (wide[:, :, 1001:] == -1.0).all() and (ewide[:, 1001:] == -1).all()
 
 
+@pytest.mark.parametrize("m", [1, 3, 16])
+def test_short_grids_use_the_lane_per_satellite_kernel_with_identical_bits(m):
+    """Grids of up to 16 times run a kernel whose lanes are satellites instead of times. Same
+    evaluation code on the same inputs: every output mode must equal, bit for bit, the same
+    times propagated as part of a long grid (lanes = times kernel), for all five orbit classes,
+    incl. failing evaluations, both time forms, the resonance node table and a padded tile."""
+    n = 2003
+    b1, b2 = pb.synth_catalog(3, n, seed=12)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    l1, l2 = ver_lines(G)
+    b = pb.SatelliteBatch.from_tles(l1 + L1, l2 + L2)
+    assert set(np.unique(b.orbit_class())) == {0, 1, 2, 3, 4}
+    long_m = 48
+    mins = np.linspace(-1500.0, 9000.0, long_m)
+    sel = np.linspace(0, long_m - 1, m).round().astype(int)
+    pl, el = b.propagate_from_epoch(mins)
+    ps, es = b.propagate_from_epoch(mins[sel].copy())
+    assert np.array_equal(es, el[:, sel]) and np.array_equal(ps, pl[:, :, sel], equal_nan=True)
+    assert (es != 0).any()  # the verification catalogue's decays and bad elements are in
+    jd, fr = pb.synth_time_grid(long_m)
+    pl, el = b.propagate(jd, fr)
+    ps, es = b.propagate(jd[sel].copy(), fr[sel].copy())
+    assert np.array_equal(es, el[:, sel]) and np.array_equal(ps, pl[:, :, sel], equal_nan=True)
+    # StateVector records, mean elements and the fused summary through the same kernel
+    sl, cl = b.propagate_states(jd, fr)
+    ss, cs = b.propagate_states(jd[sel].copy(), fr[sel].copy())
+    assert np.array_equal(cs, cl[:, sel])
+    for f in ("epoch_jd", "epoch_jd_frac", "position", "velocity"):
+        assert np.array_equal(ss[f], sl[f][:, sel], equal_nan=True), f
+    pe_l, ee_l, me_l = b.propagate_elements(mins)
+    pe_s, ee_s, me_s = b.propagate_elements(mins[sel].copy())
+    assert np.array_equal(me_s.cpu().numpy(), me_l.cpu().numpy()[:, :, sel], equal_nan=True)
+    assert np.array_equal(pe_s.cpu().numpy(), pe_l.cpu().numpy()[:, :, sel], equal_nan=True)
+    summ = b.propagate_summary(mins[sel].copy())
+    full_p, full_e = b.propagate_from_epoch(mins[sel].copy())
+    rr = np.sqrt((full_p[0:3] ** 2).sum(0))
+    ok = full_e == 0
+    assert np.array_equal(summ["n_ok"], ok.sum(1))
+    has = ok.any(1)
+    want_min = np.where(ok, rr, np.inf).min(1)
+    # (the kernel's |r| contracts its sum of squares into FMAs: equal to numpy's within an ulp)
+    assert np.abs(summ["r_min"][has] / want_min[has] - 1.0).max() < 1e-15
+    assert np.array_equal(summ["k_min"][has], np.where(ok, rr, np.inf).argmin(1)[has])
+    bad = (~ok).any(1)
+    assert np.array_equal(summ["k_first_error"][bad], (~ok).argmax(1)[bad])
+    assert (summ["k_first_error"][~bad] == -1).all()
+
+
 def test_input_order_does_not_matter():
     """The class sort is invisible: results come back in caller order, bit for bit."""
     L1, L2 = _mixed_batch(2500)
