@@ -262,7 +262,10 @@ sgp4_prop_kernel(const PropParams p) {
     const size_t sat0 = static_cast<size_t>(stile) * PB_TILE_SATS;
 
     // ---- stage constants (coalesced 256 B rows) and this CTA's slice of the time grid ----
-    for (int r = warp; r < TF::kRows; r += kWarps) {
+    // (a grid that fits one time tile is launched with just the warps it fills: blockDim.x
+    // may be below kThreads, so the staging loops go by the actual CTA size)
+    const int n_warps = static_cast<int>(blockDim.x >> 5);
+    for (int r = warp; r < TF::kRows; r += n_warps) {
         const int f = r < TF::kEndA ? r : r - TF::kEndA + TF::kBeginB;
         s_pf[lane * kRowsPad + r] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + lane];
     }
@@ -274,7 +277,7 @@ sgp4_prop_kernel(const PropParams p) {
                                        static_cast<int>(rs) * p.res_cap, 0);
     }
     const int k_base = ttile * kTimeTile;
-    for (int i = threadIdx.x; i < kTimeTile; i += kThreads) {
+    for (int i = threadIdx.x; i < static_cast<int>(blockDim.x) * kTpl; i += blockDim.x) {
         // Lanes past the end of the grid re-evaluate the last time (never stored): a made-up
         // time such as 0 would be ~1e9 minutes from epoch and spin the resonance integrator.
         const int k = min(k_base + i, p.m - 1);
@@ -607,14 +610,23 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
         } else {
             sgp4_prop_short_kernel<CLS, kModeStates><<<sb, kThreads, 0, stream>>>(p, tiles);
         }
-    } else if (p.partials != nullptr) {
-        sgp4_prop_kernel<CLS, kModeSummary><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
-    } else if (p.states != nullptr) {
-        sgp4_prop_kernel<CLS, kModeRecords><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
-    } else if (p.elements != nullptr) {
-        sgp4_prop_kernel<CLS, kModeElements><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
     } else {
-        sgp4_prop_kernel<CLS, kModeStates><<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(p);
+        // one time tile that the grid does not fill: CTAs of only the warps with work, so an SM
+        // holds 4x / 2x as many satellite tiles (32 times: 28 busy warps per SM instead of 7)
+        unsigned threads = kThreads;
+        if (p.n_time_tiles == 1) {
+            threads = 32u * static_cast<unsigned>((p.m + 32 * kTpl - 1) / (32 * kTpl));
+        }
+        const unsigned nb = static_cast<unsigned>(blocks);
+        if (p.partials != nullptr) {
+            sgp4_prop_kernel<CLS, kModeSummary><<<nb, threads, 0, stream>>>(p);
+        } else if (p.states != nullptr) {
+            sgp4_prop_kernel<CLS, kModeRecords><<<nb, threads, 0, stream>>>(p);
+        } else if (p.elements != nullptr) {
+            sgp4_prop_kernel<CLS, kModeElements><<<nb, threads, 0, stream>>>(p);
+        } else {
+            sgp4_prop_kernel<CLS, kModeStates><<<nb, threads, 0, stream>>>(p);
+        }
     }
     if (forked) {
         cudaEventRecord(l.join[CLS], stream);

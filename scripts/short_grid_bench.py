@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Short time grids (a whole catalogue at one epoch, or a few): device-timed evaluations/s of
-perturb_gpu_propagate for m = 1, 2, 4, 8, 16, 17, 32 on the mixed 100k catalogue. Prints one
+perturb_gpu_propagate for m = 1 .. 256 on the mixed 100k catalogue. Prints one
 JSON line; PERTURB_GPU_LIB selects a library variant."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,7 +16,7 @@ def main():
     batch = pb.SatelliteBatch.from_text(b1, b2, pb.WGS72, "i", device=0, n=n)
     s = torch.cuda.current_stream(dev)
     res = {}
-    for m in (1, 2, 4, 8, 16, 17, 32):
+    for m in (1, 2, 4, 8, 16, 17, 32, 64, 96, 128, 256):
         jd, fr = pb.synth_time_grid(m)
         d_jd, d_fr = torch.tensor(jd, device=dev), torch.tensor(fr, device=dev)
         out = torch.empty((6, n, m), dtype=torch.float64, device=dev)
