@@ -240,7 +240,12 @@ __device__ __forceinline__ void merge_summary(LaneSummary &a, const LaneSummary 
     }
 }
 
-template <int CLS, int MODE>
+// SPLIT: for a grid of at most 64 times (one time tile that it does not fill) the four warps
+// of a CTA also split the tile's SATELLITES -- 4 (2) warps share a group of 32 times and take
+// every 4th (2nd) satellite -- instead of leaving warps idle and the rest with all 32
+// satellites to walk one after the other. A separate instantiation: the variable loop bounds
+// cost the long-grid kernel registers (16 bytes of spills, 9 % slower when tried in place).
+template <int CLS, int MODE, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR
                                            : (CLS == PB_CLS_DEEP_R2) ? PB_MIN_BLOCKS_R2
                                                                      : PB_MIN_BLOCKS_DEEP)
@@ -289,8 +294,15 @@ sgp4_prop_kernel(const PropParams p) {
     // Lane l of warp w owns time w*32 + l of the tile (with PB_TPL = 2: w*64 + l and
     // w*64 + 32 + l): every evaluation of a warp covers 32 CONSECUTIVE times, so its stores are
     // 256 contiguous bytes per plane (full sectors) issued right after the evaluation.
-    const int i0 = warp * (32 * kTpl) + lane;
-    if (k_base + warp * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
+    int tgroup = warp, sat_first = 0, sat_step = 1;
+    if (SPLIT) {  // launched only with kTpl == 1, one time tile and m <= 64
+        const int groups = (p.m <= 32) ? 1 : 2;
+        tgroup = warp % groups;
+        sat_first = warp / groups;
+        sat_step = kWarps / groups;
+    }
+    const int i0 = tgroup * (32 * kTpl) + lane;
+    if (k_base + tgroup * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
     // (With PB_TPL = 2, skipping the second group of 32 times when only it lies beyond the grid
     // was measured: a data-dependent trip count makes ptxas treat the body as divergent, +1.4 %
     // instructions per evaluation; one time per lane avoids the question.)
@@ -304,7 +316,7 @@ sgp4_prop_kernel(const PropParams p) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
 #pragma unroll 1
-    for (int s = 0; s < PB_TILE_SATS; ++s) {
+    for (int s = SPLIT ? sat_first : 0; s < PB_TILE_SATS; s += SPLIT ? sat_step : 1) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
         const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
@@ -446,7 +458,7 @@ sgp4_prop_kernel(const PropParams p) {
                 out.first_error = acc.code_err;
                 out.k_first_error = acc.k_err;
                 out.reserved = 0;
-                p.partials[static_cast<size_t>(dst) * p.chunks + (ttile * kWarps + warp)] = out;
+                p.partials[static_cast<size_t>(dst) * p.chunks + (ttile * kWarps + tgroup)] = out;
             }
         }
     }
@@ -459,9 +471,10 @@ sgp4_prop_kernel(const PropParams p) {
 // the times). The evaluation is the same code on the same inputs, so the result of a
 // (satellite, time) pair is bit-identical to the other kernel's (tested).
 #ifndef PB_SHORT_GRID
-#define PB_SHORT_GRID 16
+#define PB_SHORT_GRID 13
 #endif
-constexpr int kShortGrid = PB_SHORT_GRID;  // grids up to this many times take this kernel
+constexpr int kShortGrid = PB_SHORT_GRID;  // grids up to this many times take this kernel (crossover
+                                          // with the SPLIT lanes = times kernel measured at 13-14)
 
 template <int CLS, int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -618,7 +631,14 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
             threads = 32u * static_cast<unsigned>((p.m + 32 * kTpl - 1) / (32 * kTpl));
         }
         const unsigned nb = static_cast<unsigned>(blocks);
-        if (p.partials != nullptr) {
+        const bool split = (kTpl == 1) && (kWarps == 4) && (p.n_time_tiles == 1) && (p.m <= 64);
+        if (split && p.partials == nullptr && p.elements == nullptr) {
+            if (p.states != nullptr) {
+                sgp4_prop_kernel<CLS, kModeRecords, true><<<nb, kThreads, 0, stream>>>(p);
+            } else {
+                sgp4_prop_kernel<CLS, kModeStates, true><<<nb, kThreads, 0, stream>>>(p);
+            }
+        } else if (p.partials != nullptr) {
             sgp4_prop_kernel<CLS, kModeSummary><<<nb, threads, 0, stream>>>(p);
         } else if (p.states != nullptr) {
             sgp4_prop_kernel<CLS, kModeRecords><<<nb, threads, 0, stream>>>(p);

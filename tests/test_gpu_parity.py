@@ -600,19 +600,21 @@ def test_time_chunking_and_strided_output_are_bit_invariant():
     assert (wide[:, :, 1001:] == -1.0).all() and (ewide[:, 1001:] == -1).all()
 
 
-@pytest.mark.parametrize("m", [1, 3, 16])
+@pytest.mark.parametrize("m", [1, 3, 16, 17, 40, 64, 70])
 def test_short_grids_use_the_lane_per_satellite_kernel_with_identical_bits(m):
-    """Grids of up to 16 times run a kernel whose lanes are satellites instead of times. Same
+    """Grids of up to 16 times run a kernel whose lanes are satellites instead of times, grids
+    of up to 64 one whose warps split the tile's satellites, up to 96 CTAs of fewer warps. Same
     evaluation code on the same inputs: every output mode must equal, bit for bit, the same
-    times propagated as part of a long grid (lanes = times kernel), for all five orbit classes,
-    incl. failing evaluations, both time forms, the resonance node table and a padded tile."""
+    times propagated as part of a long grid (the plain lanes = times kernel), for all five
+    orbit classes, incl. failing evaluations, both time forms, the resonance node table and a
+    padded tile."""
     n = 2003
     b1, b2 = pb.synth_catalog(3, n, seed=12)
     L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
     l1, l2 = ver_lines(G)
     b = pb.SatelliteBatch.from_tles(l1 + L1, l2 + L2)
     assert set(np.unique(b.orbit_class())) == {0, 1, 2, 3, 4}
-    long_m = 48
+    long_m = 200
     mins = np.linspace(-1500.0, 9000.0, long_m)
     sel = np.linspace(0, long_m - 1, m).round().astype(int)
     pl, el = b.propagate_from_epoch(mins)
