@@ -632,9 +632,13 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
         }
         const unsigned nb = static_cast<unsigned>(blocks);
         const bool split = (kTpl == 1) && (kWarps == 4) && (p.n_time_tiles == 1) && (p.m <= 64);
-        if (split && p.partials == nullptr && p.elements == nullptr) {
-            if (p.states != nullptr) {
+        if (split) {
+            if (p.partials != nullptr) {
+                sgp4_prop_kernel<CLS, kModeSummary, true><<<nb, kThreads, 0, stream>>>(p);
+            } else if (p.states != nullptr) {
                 sgp4_prop_kernel<CLS, kModeRecords, true><<<nb, kThreads, 0, stream>>>(p);
+            } else if (p.elements != nullptr) {
+                sgp4_prop_kernel<CLS, kModeElements, true><<<nb, kThreads, 0, stream>>>(p);
             } else {
                 sgp4_prop_kernel<CLS, kModeStates, true><<<nb, kThreads, 0, stream>>>(p);
             }
