@@ -80,6 +80,21 @@ def test_argument_validation_without_gpu():
     assert L.perturb_gpu_size(None) == 0
     assert L.perturb_gpu_parse_tles(None, None, 70, 1, 0, None, None) == -1
     assert L.perturb_gpu_parse_tles(b"x" * 70, b"y" * 70, 10, 1, 0, (capi.Tle * 1)(), None) == -1
+    L.perturb_gpu_parse_tle.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(capi.Tle), C.c_void_p]
+    assert L.perturb_gpu_parse_tle(None, b"y" * 70, (capi.Tle * 1)(), None) == -1
+    assert L.perturb_gpu_parse_tle(b"short", b"y" * 70, (capi.Tle * 1)(), None) == 2  # INVALID_FORMAT
+    assert L.perturb_gpu_copy(None, None, 8) == -1 and L.perturb_gpu_copy(None, None, 0) == 0
+    p = C.c_void_p(1)
+    assert L.perturb_gpu_device_alloc(0, 0, C.byref(p)) == 0 and p.value is None
+    assert L.perturb_gpu_device_alloc(0, 64, None) == -1
+    L.perturb_gpu_device_free(0, None)  # a no-op, like free(NULL)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
+def test_device_memory_helpers_fail_loudly_without_a_gpu():
+    p = C.c_void_p()
+    st = capi.lib().perturb_gpu_device_alloc(0, 1 << 20, C.byref(p))
+    assert st in (-3, -4) and p.value is None  # NODEV / ALLOC, never a silent host buffer
 
 
 # ---- TLE front end ---------------------------------------------------------------------
