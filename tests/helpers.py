@@ -133,10 +133,20 @@ def make_tle(satnum, epoch_year2, epoch_day, inc_deg, raan_deg, ecc, argp_deg, m
 def tle_parser_feed():
     """Deterministic text fed to tests/cpp/tle_members.cpp: the verification catalogue, the ISS
     example and synthetic TLEs as they are, then 30 000 corrupted pairs (characters replaced,
-    runs blanked, tails shifted) over the alphabet a damaged TLE plausibly holds."""
-    import random
+    runs blanked, tails shifted) over the alphabet a damaged TLE plausibly holds. Uses its own
+    generator (xorshift64*), so the golden hash does not depend on a library's random stream."""
     import perturb_b200 as pb
-    rnd = random.Random(7)
+    state = [0x9E3779B97F4A7C15]
+
+    def nxt(bound):
+        x = state[0]
+        x ^= (x >> 12)
+        x ^= (x << 25) & 0xFFFFFFFFFFFFFFFF
+        x ^= (x >> 27)
+        state[0] = x
+        return ((x * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF) >> 11 if bound is None else \
+            (((x * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF) >> 33) % bound
+
     here = os.path.dirname(os.path.abspath(__file__))
     lines = [ln.rstrip("\n") for ln in open(os.path.join(here, "golden", "SGP4-VER.TLE"))
              if ln[:1] in "12"]
@@ -150,19 +160,19 @@ def tle_parser_feed():
     alpha = " 0123456789.+-UAZ"
     out = [x for p in pairs for x in p]
     for _ in range(30000):
-        a, b = rnd.choice(pairs)
+        a, b = pairs[nxt(len(pairs))]
         a, b = list(a), list(b)
-        for _ in range(rnd.choice([1, 1, 1, 2, 3])):
-            L = a if rnd.random() < 0.5 else b
-            pos = rnd.randrange(69)
-            mode = rnd.random()
-            if mode < 0.6:
-                L[pos] = rnd.choice(alpha)
-            elif mode < 0.8:
-                for j in range(pos, min(69, pos + rnd.randint(1, 6))):
+        for _ in range((1, 1, 1, 2, 3)[nxt(5)]):
+            L = a if nxt(2) == 0 else b
+            pos = nxt(69)
+            mode = nxt(10)
+            if mode < 6:
+                L[pos] = alpha[nxt(len(alpha))]
+            elif mode < 8:
+                for j in range(pos, min(69, pos + 1 + nxt(6))):
                     L[j] = " "
             else:
                 L[pos + 1:] = L[pos:-1]
-                L[pos] = rnd.choice(alpha)
+                L[pos] = alpha[nxt(len(alpha))]
         out += ["".join(a), "".join(b)]
     return ("\n".join(out) + "\n").encode()
