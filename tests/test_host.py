@@ -179,3 +179,15 @@ def test_synth_full_size_fingerprint():
     assert h == again
     jd, fr = pb.synth_time_grid(1440)
     assert jd[0] == 2461317.5 and fr[1] == 1.0 / 1440.0 and fr[-1] == 1439.0 / 1440.0
+
+
+def test_abi_headers_are_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: both headers compile as C99 with -Wpedantic -Werror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "perturb_gpu.h"\n#include "perturb_synth.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only",
+                           "-I" + os.path.join(ROOT, "include"), str(src)])
