@@ -127,15 +127,18 @@ struct JulianDate {
 
     /// Whole days in `jd` (at midnight, x.5), a [0, 1) offset in `jd_frac` (perturb.cpp:60-73).
     void normalize() {
-        const double frac_days = jd - std::floor(jd) - 0.5;
-        if (std::fabs(frac_days) > 1e-12) {
-            jd -= frac_days;
-            jd_frac += frac_days;
+        // a fraction of a day hiding in `jd` (anything off the x.5 midnight grid by more than
+        // 1e-12) moves into `jd_frac` ...
+        const double off_grid = jd - std::floor(jd) - 0.5;
+        if (std::fabs(off_grid) > 1e-12) {
+            jd = jd - off_grid;
+            jd_frac = jd_frac + off_grid;
         }
+        // ... and whole days hiding in `jd_frac` move into `jd`
         if (std::fabs(jd_frac) >= 1.0) {
-            const double whole_days = std::floor(jd_frac);
-            jd += whole_days;
-            jd_frac -= whole_days;
+            const double days = std::floor(jd_frac);
+            jd = jd + days;
+            jd_frac = jd_frac - days;
         }
     }
     JulianDate normalized() const {
