@@ -274,8 +274,8 @@ def run_gpu(args):
     sp = stream.cuda_stream
 
     peak = pb.capi.C.c_double(0.0)
-    pb.capi.check(pb.capi.lib().perturb_gpu_measure_fp64_peak(local, pb.capi.C.byref(peak)),
-                  "perturb_gpu_measure_fp64_peak")
+    if pb.capi.tools().perturb_gpu_measure_fp64_peak(local, pb.capi.C.byref(peak)) != 0:
+        raise SystemExit("bench.py: perturb_gpu_measure_fp64_peak failed")
     fp64_peak = peak.value
 
     def step():

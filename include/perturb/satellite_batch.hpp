@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../perturb_gpu.h"
@@ -118,12 +119,11 @@ public:
     }
 
     /// Batched `Satellite::propagate(jd, sv)` for every satellite and every time.
-    /// `svs` and `errs` are satellite-major [size() * m]. The device writes the 64-byte
-    /// `StateVector` records themselves (perturb_gpu_propagate_states), which are copied
-    /// straight into `svs`; `sv.epoch` is always set and position / velocity are left untouched
-    /// for error codes 1-4, exactly like the reference (sgp4.cpp:1865,1878,1943,1995) -- the
-    /// few rows that contain such an evaluation are found beforehand with the fused summary
-    /// pass, saved, and put back afterwards.
+    /// `svs` and `errs` are satellite-major [size() * m], any host memory (`errs` may be null).
+    /// The device writes the 64-byte `StateVector` records themselves; they reach `svs` through
+    /// pinned bounce buffers and a few host threads (perturb_gpu_propagate_into). `sv.epoch` is
+    /// always set and position / velocity are left untouched for error codes 1-4, exactly like
+    /// the reference (sgp4.cpp:1865,1878,1943,1995).
     int propagate(const JulianDate *times, std::size_t m, StateVector *svs, Sgp4Error *errs) {
         std::vector<double> jd(m), frac(m);
         for (std::size_t k = 0; k < m; ++k) {
@@ -263,60 +263,12 @@ private:
         if (n_ == 0 || m == 0) {
             return status_ = PERTURB_GPU_OK;
         }
-        std::vector<Sgp4Error> own_errs;
-        if (errs == nullptr) {
-            own_errs.resize(n_ * m);
-            errs = own_errs.data();
-        }
-        // rows with an evaluation that is not NONE (rare: decays, bad elements)
-        std::vector<perturb_gpu_summary> summary(n_);
-        status_ = perturb_gpu_propagate_summary(handle_, ta, tb, m, summary.data(), nullptr);
-        if (status_ == PERTURB_GPU_OK) {
-            status_ = perturb_gpu_synchronize(handle_);
-        }
-        if (status_ != PERTURB_GPU_OK) {
-            return status_;
-        }
-        std::vector<std::size_t> rows;
-        for (std::size_t i = 0; i < n_; ++i) {
-            if (static_cast<std::size_t>(summary[i].n_ok) != m) {
-                rows.push_back(i);
-            }
-        }
-        std::vector<StateVector> saved(rows.size() * m);
-        for (std::size_t r = 0; r < rows.size(); ++r) {
-            for (std::size_t k = 0; k < m; ++k) {
-                saved[r * m + k] = svs[rows[r] * m + k];
-            }
-        }
-        std::vector<StateVector> bounce;  // only if the caller's array is not 16-byte aligned
-        StateVector *dst = svs;
-        if ((reinterpret_cast<std::uintptr_t>(svs) & 15u) != 0) {
-            bounce.resize(n_ * m + 1);
-            dst = bounce.data();
-            if ((reinterpret_cast<std::uintptr_t>(dst) & 15u) != 0) {
-                dst = reinterpret_cast<StateVector *>(reinterpret_cast<char *>(dst) + 8);
-            }
-        }
-        if (propagate_states(ta, tb, m, dst, errs, m, nullptr) != PERTURB_GPU_OK) {
-            return status_;
-        }
-        if (dst != svs) {
-            for (std::size_t e = 0; e < n_ * m; ++e) {
-                svs[e] = dst[e];
-            }
-        }
-        for (std::size_t r = 0; r < rows.size(); ++r) {
-            for (std::size_t k = 0; k < m; ++k) {
-                const std::size_t e = rows[r] * m + k;
-                const int code = static_cast<int>(errs[e]);
-                if (code != 0 && code != 6) {  // the reference writes r, v for NONE and DECAYED only
-                    svs[e].position = saved[r * m + k].position;
-                    svs[e].velocity = saved[r * m + k].velocity;
-                }
-            }
-        }
-        return status_;
+        // perturb_gpu_propagate_into keeps the reference's semantics itself: epoch always set,
+        // position / velocity stored for NONE and DECAYED only, any host memory as destination.
+        return status_ = perturb_gpu_propagate_into(
+                   handle_, ta, tb, m, reinterpret_cast<perturb_gpu_state *>(svs),
+                   reinterpret_cast<std::int32_t *>(errs), m
+               );
     }
 
     perturb_gpu_batch *handle_;
@@ -359,6 +311,48 @@ public:
         }
     }
 
+    /// Batched `Satellite::from_tle(line_1, line_2, grav)` over several devices: the lines are
+    /// read once on the host (Vallado's numeric conventions, as `SatelliteBatch::from_tles`)
+    /// to place the range boundaries, then every shard parses its own range on its device.
+    static ShardedSatelliteBatch from_tles(
+        const std::string *lines_1, const std::string *lines_2, std::size_t n, const int *devices,
+        std::size_t n_devices, GravModel grav_model = GravModel::WGS72
+    ) {
+        ShardedSatelliteBatch out;
+        out.n_ = n;
+        if (n_devices == 0) {
+            out.status_ = PERTURB_GPU_ERR_ARG;
+            return out;
+        }
+        std::vector<double> cost(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            perturb_gpu_tle numbers;
+            const bool readable = lines_1[i].size() >= 69 && lines_2[i].size() >= 69 &&
+                perturb_gpu_parse_tles(lines_1[i].c_str(), lines_2[i].c_str(), 70, 1, 1,
+                                       &numbers, nullptr) == PERTURB_GPU_OK;
+            TwoLineElement t = TwoLineElement();
+            if (readable) {
+                t.mean_motion = numbers.mean_motion;
+                t.eccentricity = numbers.eccentricity;
+            }
+            cost[i] = estimated_cost(t);
+        }
+        out.cuts_ = plan_ranges(cost, n_devices);
+        for (std::size_t s = 0; s < n_devices; ++s) {
+            out.shards_.push_back(SatelliteBatch::from_tles(
+                lines_1 + out.cuts_[s], lines_2 + out.cuts_[s], out.cuts_[s + 1] - out.cuts_[s],
+                grav_model, devices[s]
+            ));
+            if (!out.shards_.back().ok()) {
+                out.status_ = out.shards_.back().status();
+            }
+        }
+        return out;
+    }
+
+    ShardedSatelliteBatch(ShardedSatelliteBatch &&) = default;
+    ShardedSatelliteBatch &operator=(ShardedSatelliteBatch &&) = default;
+
     bool ok() const { return status_ == PERTURB_GPU_OK; }
     int status() const { return status_; }
     std::size_t size() const { return n_; }
@@ -375,6 +369,30 @@ public:
     JulianDate epoch(std::size_t i) const {
         const std::size_t s = shard_of(i);
         return s < shards_.size() ? shards_[s].epoch(i - cuts_[s]) : JulianDate();
+    }
+
+    /// The drop-in call, `Satellite::propagate(jd, sv)` (perturb.cpp:236-242) for every
+    /// satellite and time into the caller's own arrays, satellite-major [size() * m]: every
+    /// shard runs `SatelliteBatch::propagate` on its rows from its own host thread, so all
+    /// devices compute, copy and scatter concurrently. Same semantics as the single-device
+    /// class: `sv.epoch` always set, position / velocity untouched for error codes 1-4.
+    int propagate(const JulianDate *times, std::size_t m, StateVector *svs, Sgp4Error *errs) {
+        return for_each_shard([&](std::size_t s) {
+            return shards_[s].propagate(
+                times, m, svs + cuts_[s] * m, errs != nullptr ? errs + cuts_[s] * m : nullptr
+            );
+        });
+    }
+
+    /// `Satellite::propagate_from_epoch(mins, sv)` (perturb.cpp:228-234), likewise.
+    int propagate_from_epoch(
+        const double *mins, std::size_t m, StateVector *svs, Sgp4Error *errs
+    ) {
+        return for_each_shard([&](std::size_t s) {
+            return shards_[s].propagate_from_epoch(
+                mins, m, svs + cuts_[s] * m, errs != nullptr ? errs + cuts_[s] * m : nullptr
+            );
+        });
     }
 
     /// `SatelliteBatch::propagate_soa` over all shards into buffers indexed by the caller's
@@ -500,6 +518,30 @@ public:
     }
 
 private:
+    ShardedSatelliteBatch() : n_(0), status_(PERTURB_GPU_OK) {}
+
+    // fn(shard) on one host thread per non-empty shard; first failure wins.
+    template <class Fn>
+    int for_each_shard(Fn fn) {
+        std::vector<int> st(shards_.size(), PERTURB_GPU_OK);
+        std::vector<std::thread> threads;
+        for (std::size_t s = 0; s < shards_.size(); ++s) {
+            if (cuts_[s + 1] == cuts_[s]) {
+                continue;
+            }
+            threads.emplace_back([&st, &fn, s]() { st[s] = fn(s); });
+        }
+        for (std::size_t t = 0; t < threads.size(); ++t) {
+            threads[t].join();
+        }
+        for (std::size_t s = 0; s < st.size(); ++s) {
+            if (st[s] != PERTURB_GPU_OK && status_ == PERTURB_GPU_OK) {
+                status_ = st[s];
+            }
+        }
+        return status_;
+    }
+
     std::size_t shard_of(std::size_t i) const {
         for (std::size_t s = 0; s + 1 < cuts_.size(); ++s) {
             if (i >= cuts_[s] && i < cuts_[s + 1]) {

@@ -145,8 +145,10 @@ int perturb_gpu_propagate_from_epoch(perturb_gpu_batch *batch, const double *min
  * 198-205: JulianDate epoch {jd, jd_frac}; Vec3 position; Vec3 velocity -- 8 doubles, 64 bytes,
  * layout asserted in include/perturb/satellite_batch.hpp) instead of structure-of-arrays planes:
  * the buffer a caller's `std::vector<StateVector>` already is.
- *   states  states[i * row_stride + k] (row_stride in records, >= m), host or device memory,
- *           16-byte aligned, satellites in caller order
+ *   states  states[i * row_stride + k] (row_stride in records, >= m), host or device memory
+ *           (device memory 16-byte aligned), satellites in caller order. Pinned host memory is
+ *           written by the copy engine and the call returns after enqueueing; pageable host
+ *           memory is filled through the handle's bounce buffers before the call returns
  *   err     err[i * row_stride + k]
  * `epoch` is always set, as the reference does: to (jd[k], jd_frac[k]) by `propagate`
  * (perturb.cpp:240), to epoch(i) + mins[k] / 1440 (operator+, perturb.cpp:85-89: added to the
@@ -162,6 +164,21 @@ typedef struct perturb_gpu_state {
 int perturb_gpu_propagate_states(perturb_gpu_batch *batch, const double *jd,
                                  const double *jd_frac, size_t m, perturb_gpu_state *states,
                                  int32_t *err, size_t row_stride, void *stream);
+
+/* The drop-in form of the loop itself,
+ *     for i, k:  errs[i * row_stride + k] = sats[i].propagate(times[k], svs[i * row_stride + k]);
+ * into the caller's own HOST arrays (any host memory: a std::vector<StateVector> is fine),
+ * with the reference's semantics for failed evaluations: `epoch` is always set, position and
+ * velocity are written for codes NONE and DECAYED only and otherwise LEFT AS THEY WERE
+ * (src/sgp4.cpp:1865,1878,1943,1995 return before the store). `err` may be NULL. Synchronous:
+ * the results are in place when the call returns. Chunks of the time grid are computed, copied
+ * into pinned bounce buffers owned by the handle and moved into the caller's arrays by a few
+ * host threads (PERTURB_GPU_HOST_THREADS, default half the hardware threads, at most 16) while
+ * the next chunk is computed and copied. jd_frac == NULL selects the `propagate_from_epoch`
+ * form with `jd` holding minutes. */
+int perturb_gpu_propagate_into(perturb_gpu_batch *batch, const double *jd, const double *jd_frac,
+                               size_t m, perturb_gpu_state *states, int32_t *err,
+                               size_t row_stride);
 
 /* Same evaluation, additionally handing back what `sgp4()` leaves in `Satellite::sat_rec` on
  * every call (src/sgp4.cpp:1895-1901): the singly averaged mean elements
@@ -259,15 +276,6 @@ int perturb_gpu_record_field(const perturb_gpu_batch *batch, int field, double *
 
 /* Number of kernel launches the last propagate call on this handle issued. */
 int perturb_gpu_last_launch_count(const perturb_gpu_batch *batch);
-
-/* FP64 roofline denominator: DFMA-only microbenchmark on `device` (no memory traffic),
- * best of 5 after a warm-up; *tflops counts a DFMA as 2 flops. Used by bench.py. */
-int perturb_gpu_measure_fp64_peak(int device, double *tflops);
-
-/* Test hook: out[i] = f(x[i], y[i]) for the device math routine number `fn` (see
- * perturb_b200/csrc/math_probe.cu); host pointers. Lets the test-suite bound the error of
- * the FP64 fast paths against correctly rounded host values. */
-int perturb_gpu_math_probe(int fn, const double *x, const double *y, double *out, size_t n);
 
 /* Message for the most recent failure on the calling thread. */
 const char *perturb_gpu_strerror(void);

@@ -55,7 +55,7 @@ def synth_catalog(config, n, seed=0):
     """Synthetic catalogue of BASELINE config `config` as two fixed-stride line blocks."""
     b1 = C.create_string_buffer(n * capi.SYNTH_LINE_STRIDE)
     b2 = C.create_string_buffer(n * capi.SYNTH_LINE_STRIDE)
-    st = capi.lib().perturb_synth_catalog(config, n, seed, b1, b2)
+    st = capi.tools().perturb_synth_catalog(config, n, seed, b1, b2)
     if st != 0:
         raise ValueError("bad synthetic catalogue arguments")
     return b1.raw, b2.raw
@@ -69,7 +69,7 @@ def synth_time_grid(m):
     jd = np.zeros(m)
     fr = np.zeros(m)
     dp = C.POINTER(C.c_double)
-    capi.lib().perturb_synth_time_grid(m, jd.ctypes.data_as(dp), fr.ctypes.data_as(dp))
+    capi.tools().perturb_synth_time_grid(m, jd.ctypes.data_as(dp), fr.ctypes.data_as(dp))
     return jd, fr
 
 

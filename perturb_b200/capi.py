@@ -1,13 +1,17 @@
-"""ctypes view of the C ABI in include/perturb_gpu.h and include/perturb_synth.h.
+"""ctypes view of the C ABI in include/perturb_gpu.h (the product, libperturb_gpu.so) and of the
+measurement tooling in include/perturb_benchtools.h / perturb_synth.h (libperturb_benchtools.so:
+synthetic catalogues, FP64 / D2H peak probes, the device-math test hook).
 
-The shared library is built in-tree (perturb_b200/libperturb_gpu.so, see csrc/Makefile).
-There is no CPU fallback: if the library is missing, loading fails loudly.
+Both libraries are built in-tree (see csrc/Makefile). There is no CPU fallback: if the product
+library is missing, loading fails loudly. `tools()` never maps the product library, so the
+benchmark's reference arm can take the synthetic catalogue without touching it.
 """
 import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PERTURB_GPU_LIB") or os.path.join(_HERE, "libperturb_gpu.so")
+TOOLS_PATH = os.path.join(_HERE, "libperturb_benchtools.so")
 
 OK = 0
 WGS72_OLD, WGS72, WGS84 = 0, 1, 2
@@ -25,18 +29,23 @@ class Tle(C.Structure):
     _fields_ = [(n, C.c_double) for n in TLE_FIELDS]
 
 
-# Every symbol include/perturb_gpu.h and include/perturb_synth.h declare.
+# Every symbol include/perturb_gpu.h declares ...
 EXPORTS = (
     "perturb_gpu_init perturb_gpu_init_from_text perturb_gpu_init_records perturb_gpu_free perturb_gpu_propagate "
     "perturb_gpu_propagate_from_epoch perturb_gpu_propagate_states perturb_gpu_propagate_elements perturb_gpu_propagate_summary perturb_gpu_rv2coe perturb_gpu_synchronize perturb_gpu_device_count perturb_gpu_host_alloc perturb_gpu_host_free perturb_gpu_device_alloc perturb_gpu_device_free perturb_gpu_copy perturb_gpu_size "
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles perturb_gpu_parse_tle "
-    "perturb_gpu_measure_fp64_peak perturb_gpu_math_probe "
+    "perturb_gpu_propagate_into"
+).split()
+# ... and include/perturb_benchtools.h + include/perturb_synth.h (libperturb_benchtools.so)
+TOOLS_EXPORTS = (
+    "perturb_gpu_measure_fp64_peak perturb_gpu_measure_d2h perturb_gpu_math_probe "
     "perturb_synth_catalog perturb_synth_time_grid"
 ).split()
 
 _lib = None
+_tools = None
 
 
 class Summary(C.Structure):
@@ -97,15 +106,30 @@ def lib():
     L.perturb_gpu_record_field.argtypes = [vp, C.c_int, dp]
     L.perturb_gpu_last_launch_count.argtypes = [vp]
     L.perturb_gpu_strerror.restype = C.c_char_p
-    L.perturb_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
-    L.perturb_gpu_math_probe.argtypes = [C.c_int, dp, dp, dp, C.c_size_t]
     L.perturb_gpu_parse_tles.argtypes = [
         C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Tle), ip]
-    L.perturb_synth_catalog.argtypes = [
-        C.c_int, C.c_size_t, C.c_uint64, C.c_char_p, C.c_char_p]
-    L.perturb_synth_time_grid.argtypes = [C.c_size_t, dp, dp]
+    L.perturb_gpu_propagate_into.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
     _lib = L
     return L
+
+
+def tools():
+    """libperturb_benchtools.so: workload generator and measurement probes (not the product)."""
+    global _tools
+    if _tools is not None:
+        return _tools
+    if not os.path.exists(TOOLS_PATH):
+        raise PerturbGpuError("%s is missing: build it with `make -C perturb_b200/csrc`" % TOOLS_PATH)
+    T = C.CDLL(TOOLS_PATH)
+    dp = C.POINTER(C.c_double)
+    T.perturb_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    T.perturb_gpu_measure_d2h.argtypes = [C.c_int, C.c_size_t, C.c_int, dp, dp]
+    T.perturb_gpu_math_probe.argtypes = [C.c_int, dp, dp, dp, C.c_size_t]
+    T.perturb_synth_catalog.argtypes = [
+        C.c_int, C.c_size_t, C.c_uint64, C.c_char_p, C.c_char_p]
+    T.perturb_synth_time_grid.argtypes = [C.c_size_t, dp, dp]
+    _tools = T
+    return T
 
 
 def check(status, what):

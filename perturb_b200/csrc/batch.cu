@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <new>
@@ -13,6 +14,7 @@
 
 #include "../../include/perturb_gpu.h"
 #include "batch_internal.h"
+#include "host_workers.h"
 
 namespace {
 
@@ -46,6 +48,18 @@ bool is_device_pointer(const void *p) {
         return false;
     }
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister): the copy engines reach it directly.
+// Anything else on the host (malloc, std::vector, numpy) is pageable.
+bool is_pinned_host_pointer(const void *p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
 }
 
 // Ordinal of the device whose memory `p` points into; -1 for host (or managed) memory.
@@ -159,6 +173,10 @@ struct perturb_gpu_batch {
     int32_t *d_stage_err[2];
     size_t stage_cap[2];  // evaluations each staging buffer holds
     cudaEvent_t ev_done[2], ev_free[2];
+    cudaEvent_t ev_call;        // end of the most recent call: the next one is ordered after it
+    void *h_bounce[2];          // pinned bounce buffers for pageable host outputs
+    size_t bounce_cap[2];       // bytes
+    pb::HostWorkers *workers;   // scatter threads (created on first use)
     double2 *d_res_nodes;  // resonance node table [resonant slots][res_cap] of 32-byte records
     int *d_res_k0, *d_res_cnt;
     double *d_res_range;
@@ -167,6 +185,7 @@ struct perturb_gpu_batch {
     cudaStream_t aux[PB_CLS_COUNT];  // forked streams, one per orbit class
     cudaEvent_t ev_fork, ev_join[PB_CLS_COUNT];
     int last_launches;
+    int cta_sats;  // tuning knob (PERTURB_GPU_CTA_SATS), 0 = automatic
     void *d_summary;  // scratch of perturb_gpu_propagate_summary
     size_t summary_cap;
 
@@ -174,7 +193,8 @@ struct perturb_gpu_batch {
         : device(0), n(0), n_pad(0), opsmode_a(false), d_rec(nullptr), d_pf(nullptr),
           d_perm(nullptr), stream(nullptr), last_stream(nullptr), copy_stream(nullptr),
           d_times(nullptr),
-          times_cap(0), last_launches(0), d_summary(nullptr), summary_cap(0) {
+          times_cap(0), last_launches(0), cta_sats(0), d_summary(nullptr), summary_cap(0) {
+        if (const char *e = std::getenv("PERTURB_GPU_CTA_SATS")) cta_sats = std::atoi(e);
         for (int c = 0; c < PB_CLS_COUNT; ++c) {
             tile_begin[c] = tile_count[c] = 0;
             aux[c] = nullptr;
@@ -191,7 +211,11 @@ struct perturb_gpu_batch {
             d_stage_err[b] = nullptr;
             stage_cap[b] = 0;
             ev_done[b] = ev_free[b] = nullptr;
+            h_bounce[b] = nullptr;
+            bounce_cap[b] = 0;
         }
+        ev_call = nullptr;
+        workers = nullptr;
     }
 };
 
@@ -210,7 +234,10 @@ void destroy(perturb_gpu_batch *b) {
         cudaFree(b->d_stage_err[i]);
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
         if (b->ev_free[i]) cudaEventDestroy(b->ev_free[i]);
+        if (b->h_bounce[i]) cudaFreeHost(b->h_bounce[i]);
     }
+    if (b->ev_call) cudaEventDestroy(b->ev_call);
+    delete b->workers;
     for (int c = 0; c < PB_CLS_COUNT; ++c) {
         if (b->aux[c]) cudaStreamDestroy(b->aux[c]);
         if (b->ev_join[c]) cudaEventDestroy(b->ev_join[c]);
@@ -329,6 +356,8 @@ int create_streams(perturb_gpu_batch *b) {
         PB_CUDA(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
     }
     PB_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&b->ev_call, cudaEventDisableTiming));
+    PB_CUDA(cudaEventRecord(b->ev_call, b->stream));
     for (int c = 0; c < PB_CLS_COUNT; ++c) {
         PB_CUDA(cudaStreamCreateWithFlags(&b->aux[c], cudaStreamNonBlocking));
         PB_CUDA(cudaEventCreateWithFlags(&b->ev_join[c], cudaEventDisableTiming));
@@ -481,12 +510,14 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
     l.j2 = b->grav.j2;
     l.j3oj2 = b->grav.j3oj2;
     l.opsmode_a = b->opsmode_a ? 1 : 0;
+    l.cta_sats = b->cta_sats;
     l.res_nodes = b->d_res_nodes;
     l.res_k0 = b->d_res_k0;
     l.res_cnt = b->d_res_cnt;
     l.res_range = b->d_res_range;
     l.res_cap = b->res_cap;
     l.fork = b->ev_fork;
+    l.fork_recorded = false;
     for (int c = 0; c < PB_CLS_COUNT; ++c) {
         l.aux[c] = b->aux[c];
         l.join[c] = b->ev_join[c];
@@ -505,20 +536,23 @@ int peer_ready(perturb_gpu_batch *b, int owner) {
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
                    size_t m, double *posvel, int32_t *err, size_t row_stride,
                    size_t plane_stride, void *stream_arg, double *elements = nullptr,
-                   bool records = false) {
+                   bool records = false, bool keep_failed = false) {
     // records: `posvel` is an array of perturb_gpu_state (8 doubles each) indexed
     // [sat * row_stride + k]; plane_stride is unused.
+    // keep_failed (records in host memory only): position / velocity of evaluations with codes
+    // 1-4 are left as the caller had them, like the reference (sgp4.cpp:1865,1878,1943,1995).
     if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
     b->last_launches = 0;
     if (m == 0 || b->n == 0) return PERTURB_GPU_OK;
-    if (ta == nullptr || (use_jd && tb == nullptr) || posvel == nullptr || err == nullptr) {
+    if (ta == nullptr || (use_jd && tb == nullptr) || posvel == nullptr ||
+        (err == nullptr && !keep_failed)) {
         return fail(PERTURB_GPU_ERR_ARG, "null time or output pointer");
     }
     if (row_stride < m || (!records && plane_stride < b->n * row_stride)) {
         return fail(PERTURB_GPU_ERR_ARG, "row_stride < m or plane_stride < n * row_stride");
     }
-    if (records && (reinterpret_cast<uintptr_t>(posvel) & 15u) != 0) {
-        return fail(PERTURB_GPU_ERR_ARG, "states must be 16-byte aligned");
+    if (records && is_device_pointer(posvel) && (reinterpret_cast<uintptr_t>(posvel) & 15u) != 0) {
+        return fail(PERTURB_GPU_ERR_ARG, "device-resident states must be 16-byte aligned");
     }
     if (m > static_cast<size_t>(1) << 30) return fail(PERTURB_GPU_ERR_ARG, "time grid too long");
     DeviceGuard guard(b->device);
@@ -526,6 +560,9 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     // NULL is the (legacy) default stream, as in the CUDA runtime API.
     cudaStream_t stream = static_cast<cudaStream_t>(stream_arg);
     b->last_stream = stream;
+    // One call at a time per handle: the scratch below (time grid, node table, staging) is the
+    // handle's, so a call on another stream is ordered after the previous one.
+    PB_CUDA(cudaStreamWaitEvent(stream, b->ev_call, 0));
 
     // ---- time grid on the device ----
     // (a grid that lives on another device is copied like a host one: it is read n / 32 times)
@@ -561,9 +598,12 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     }
 
     const bool out_dev = is_device_pointer(posvel);
-    const bool err_dev = is_device_pointer(err);
+    const bool err_dev = (err != nullptr) ? is_device_pointer(err) : out_dev;
     if (out_dev != err_dev) {
         return fail(PERTURB_GPU_ERR_ARG, "posvel and err must both be host or both be device");
+    }
+    if (keep_failed && (out_dev || !records)) {
+        return fail(PERTURB_GPU_ERR_ARG, "keep_failed needs StateVector records in host memory");
     }
 
     if (out_dev) {
@@ -583,30 +623,114 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         l.err = err;
         l.err_row_stride = row_stride;
         b->last_launches = pb::launch_sgp4_propagate(l, stream);
+        if (b->last_launches < 0) {
+            b->last_launches = 0;
+            return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+        }
         PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaEventRecord(b->ev_call, stream));
         return PERTURB_GPU_OK;
     }
 
     // ---- host outputs: time-chunked, double-buffered device staging + async D2H ----
+    // Pinned destinations are written by the copy engine directly (asynchronous call);
+    // pageable ones (std::vector, numpy) go through pinned bounce buffers that host threads
+    // scatter into the caller's arrays while the next chunk is computed and copied (the call
+    // returns when the results are in place).
+    const bool direct = !keep_failed && is_pinned_host_pointer(posvel) && is_pinned_host_pointer(err);
     size_t free_b = 0, total_b = 0;
     PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t dpe = records ? 8 : 6;  // doubles per evaluation in the staging buffer
     const size_t bytes_per_eval = dpe * sizeof(double) + sizeof(int32_t);
     size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(8) << 30);  // per buffer
     for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * bytes_per_eval);
+    // The copy takes ~40x as long as the kernel (PCIe 55 GB/s against 2 TB/s of output): at least
+    // four chunks, so that all but the first kernel hides behind a copy; bounce chunks of
+    // ~128 MiB, whole time tiles of kernel 2 where that is possible.
+    const size_t total_bytes = bytes_per_eval * b->n * m;
+    if (direct && total_bytes > (static_cast<size_t>(64) << 20)) {
+        budget = std::min(budget, std::max<size_t>(total_bytes / 4, static_cast<size_t>(16) << 20));
+    }
+    if (!direct) budget = std::min(budget, static_cast<size_t>(128) << 20);
     const size_t m_even = (m + 1) & ~static_cast<size_t>(1);
     size_t fit = budget / (bytes_per_eval * b->n);  // times one staging buffer can hold
+    if (fit >= 256) fit &= ~static_cast<size_t>(127);
     fit &= ~static_cast<size_t>(1);
     if (fit < 2) fit = 2;
     // Balanced chunks (not "full, full, ..., sliver"): short rows make poor 2-D copies.
     const size_t nchunks = (m_even + fit - 1) / fit;
     size_t mc = ((m + nchunks - 1) / nchunks + 1) & ~static_cast<size_t>(1);  // even
+    if (mc >= 256 && nchunks > 1) mc = std::min(fit, (mc + 127) & ~static_cast<size_t>(127));
     const size_t mc_pad = mc;
     const int nbuf = nchunks > 1 ? 2 : 1;
     for (int i = 0; i < nbuf; ++i) {
-        int st = ensure_stage(b, i, b->n * mc_pad, dpe);
+        // (bounce chunks keep their error codes behind the states in the same block)
+        int st = ensure_stage(b, i, b->n * mc_pad, direct ? dpe : dpe + 1);
         if (st != PERTURB_GPU_OK) return st;
+        if (!direct) {
+            const size_t need = b->n * mc_pad * bytes_per_eval;
+            if (b->bounce_cap[i] < need) {
+                if (b->h_bounce[i]) cudaFreeHost(b->h_bounce[i]);
+                b->h_bounce[i] = nullptr;
+                b->bounce_cap[i] = 0;
+                if (cudaHostAlloc(&b->h_bounce[i], need, cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(PERTURB_GPU_ERR_ALLOC, "pinned bounce buffer allocation failed");
+                }
+                b->bounce_cap[i] = need;
+            }
+        }
     }
+    if (!direct && b->workers == nullptr) {
+        unsigned threads = pb::default_host_workers();
+        if (const char *e = std::getenv("PERTURB_GPU_HOST_THREADS")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 256) threads = static_cast<unsigned>(v);
+        }
+        b->workers = new (std::nothrow) pb::HostWorkers(threads);
+        if (b->workers == nullptr) return fail(PERTURB_GPU_ERR_ALLOC, "host allocation failed");
+    }
+
+    // Bounce chunk -> the caller's arrays (rows of one chunk, host threads).
+    struct Pending {
+        bool valid;
+        int buf;
+        size_t k0, mk, ld;
+    } pending = {false, 0, 0, 0, 0};
+    auto scatter = [&](const Pending &pc) {
+        const size_t n = b->n;
+        const char *src = static_cast<const char *>(b->h_bounce[pc.buf]);
+        const int32_t *src_err = reinterpret_cast<const int32_t *>(src + n * pc.ld * dpe * sizeof(double));
+        const size_t k0 = pc.k0, mk = pc.mk, ld = pc.ld;
+        b->workers->parallel_for(n, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const int32_t *ei = src_err + i * ld;
+                if (err != nullptr) std::memcpy(err + i * row_stride + k0, ei, mk * sizeof(int32_t));
+                if (records) {
+                    const char *si = src + i * ld * 64;
+                    char *di = reinterpret_cast<char *>(posvel) + (i * row_stride + k0) * 64;
+                    bool clean = true;
+                    if (keep_failed) {
+                        for (size_t k = 0; k < mk; ++k) clean = clean && (ei[k] == 0 || ei[k] == 6);
+                    }
+                    if (clean) {
+                        std::memcpy(di, si, mk * 64);
+                    } else {
+                        for (size_t k = 0; k < mk; ++k) {  // epoch always, r / v for codes 0 and 6
+                            const bool written = (ei[k] == 0 || ei[k] == 6);
+                            std::memcpy(di + k * 64, si + k * 64, written ? 64 : 16);
+                        }
+                    }
+                } else {
+                    for (size_t pl = 0; pl < 6; ++pl) {
+                        std::memcpy(posvel + pl * plane_stride + i * row_stride + k0,
+                                    src + (pl * n * ld + i * ld) * sizeof(double), mk * sizeof(double));
+                    }
+                }
+            }
+        });
+    };
+
     for (size_t c = 0; c < nchunks; ++c) {
         const int buf = static_cast<int>(c % 2);
         const size_t k0 = c * mc;
@@ -620,15 +744,34 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         l.states = records ? b->d_stage[buf] : nullptr;
         // one chunk covering whole contiguous caller rows: stage with the caller's own
         // strides so that the D2H is a single linear copy per buffer
-        const bool linear = (nchunks == 1) && (row_stride == m) && (m % 2 == 0);
-        l.row_stride = linear ? m : mc_pad;
+        const bool linear = direct && (nchunks == 1) && (row_stride == m) && (m % 2 == 0);
+        // bounce chunks are packed (row length = the chunk's own, rounded up to even)
+        l.row_stride = linear ? m : direct ? mc_pad : ((mk + 1) & ~static_cast<size_t>(1));
         l.plane_stride = b->n * l.row_stride;
-        l.err = b->d_stage_err[buf];
+        l.err = direct ? b->d_stage_err[buf]
+                       : reinterpret_cast<int32_t *>(b->d_stage[buf] + b->n * l.row_stride * dpe);
         l.err_row_stride = l.row_stride;
-        b->last_launches += pb::launch_sgp4_propagate(l, stream);
+        const int launched = pb::launch_sgp4_propagate(l, stream);
+        if (launched < 0) {
+            return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+        }
+        b->last_launches += launched;
         PB_CUDA(cudaGetLastError());
         PB_CUDA(cudaEventRecord(b->ev_done[buf], stream));
         PB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
+        if (!direct) {
+            // states and codes of the chunk are one contiguous block of the staging buffer
+            PB_CUDA(cudaMemcpyAsync(b->h_bounce[buf], b->d_stage[buf],
+                                    b->n * l.row_stride * bytes_per_eval, cudaMemcpyDeviceToHost,
+                                    b->copy_stream));
+            PB_CUDA(cudaEventRecord(b->ev_free[buf], b->copy_stream));
+            if (pending.valid) {  // the previous chunk, while this one is computed and copied
+                PB_CUDA(cudaEventSynchronize(b->ev_free[pending.buf]));
+                scatter(pending);
+            }
+            pending = {true, buf, k0, mk, l.row_stride};
+            continue;
+        }
         if (records) {
             // rows of 64-byte records: one 2-D copy (or a linear one when the rows are whole)
             const size_t rb = 8 * sizeof(double);
@@ -675,10 +818,15 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
         }
         PB_CUDA(cudaEventRecord(b->ev_free[buf], b->copy_stream));
     }
+    if (pending.valid) {
+        PB_CUDA(cudaEventSynchronize(b->ev_free[pending.buf]));
+        scatter(pending);
+    }
     // The caller's stream must see the copies as part of this call.
     const int last = static_cast<int>((nchunks - 1) % 2);
     PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[last], 0));
     if (nchunks > 1) PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[1 - last], 0));
+    PB_CUDA(cudaEventRecord(b->ev_call, stream));
     return PERTURB_GPU_OK;
 }
 
@@ -731,6 +879,16 @@ int perturb_gpu_propagate_states(perturb_gpu_batch *batch, const double *jd,
     return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m,
                           reinterpret_cast<double *>(states), err, row_stride, 0, stream, nullptr,
                           true);
+}
+
+int perturb_gpu_propagate_into(perturb_gpu_batch *batch, const double *jd, const double *jd_frac,
+                               size_t m, perturb_gpu_state *states, int32_t *err,
+                               size_t row_stride) {
+    const int st = propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m,
+                                  reinterpret_cast<double *>(states), err, row_stride, 0, nullptr,
+                                  nullptr, true, true);
+    if (st != PERTURB_GPU_OK) return st;
+    return perturb_gpu_synchronize(batch);
 }
 
 int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
@@ -805,6 +963,10 @@ int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const 
     l.summary_out = out_dev ? out : folded;
     l.n = b->n;
     b->last_launches = pb::launch_sgp4_propagate(l, stream);
+    if (b->last_launches < 0) {
+        b->last_launches = 0;
+        return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+    }
     PB_CUDA(cudaGetLastError());
     if (!out_dev) {
         PB_CUDA(cudaMemcpyAsync(out, folded, b->n * sizeof(perturb_gpu_summary),

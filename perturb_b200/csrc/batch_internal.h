@@ -60,6 +60,7 @@ struct PropLaunch {
     size_t n;                // satellites (caller count), needed by the reduce pass
     double radiusearthkm, xke, j2, j3oj2;
     int opsmode_a;
+    int cta_sats;  // satellites per CTA of kernel 2 (32 / 16 / 8; 0 = chosen from the grid size)
     // resonance node table scratch (null / 0: resonant evaluations integrate in-line)
     double2 *res_nodes;  // [resonant slots][res_cap] records {xli, xni, xndt, xnddt} (2 double2 each)
     int *res_k0, *res_cnt;
@@ -68,10 +69,12 @@ struct PropLaunch {
     // optional fork/join resources so class launches overlap (null = serial on one stream)
     cudaStream_t aux[PB_CLS_COUNT];
     cudaEvent_t fork;
+    bool fork_recorded;  // set by launch_sgp4_propagate
     cudaEvent_t join[PB_CLS_COUNT];
 };
 
-// Kernel 2, one launch per non-empty class. Returns the number of launches issued.
+// Kernel 2, one launch per non-empty class. Returns the number of launches issued, or -1 when
+// the grid (satellite tiles x time tiles) exceeds what one launch can cover.
 int launch_sgp4_propagate(const PropLaunch &p, cudaStream_t stream);
 
 // Number of per-satellite partial records the summary mode needs for a grid of m times.

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/perturb_gpu.h"
+#include "../../include/perturb_benchtools.h"
 
 namespace {
 
@@ -63,5 +64,55 @@ extern "C" int perturb_gpu_measure_fp64_peak(int device, double *tflops) {
     if (prev >= 0) cudaSetDevice(prev);
     if (err != cudaSuccess) return PERTURB_GPU_ERR_CUDA;
     *tflops = best * 1e-12;
+    return PERTURB_GPU_OK;
+}
+
+// Raw D2H rate into pinned host memory: the ceiling of every host-buffer (end-to-end) figure.
+extern "C" int perturb_gpu_measure_d2h(int device, size_t bytes, int reps, double *gbs_best,
+                                       double *gbs_mean) {
+    if (gbs_best == nullptr || bytes == 0 || reps < 1) return PERTURB_GPU_ERR_ARG;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) return PERTURB_GPU_ERR_NODEV;
+    void *d = nullptr, *h = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int status = PERTURB_GPU_OK;
+    double best = 0.0, total_ms = 0.0;
+    if (cudaMalloc(&d, bytes) != cudaSuccess || cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        status = PERTURB_GPU_ERR_ALLOC;
+    } else if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+               cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        status = PERTURB_GPU_ERR_CUDA;
+    } else {
+        cudaMemsetAsync(d, 1, bytes, stream);
+        cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream);  // warm-up: first touch
+        cudaStreamSynchronize(stream);
+        for (int r = 0; r < reps; ++r) {
+            cudaEventRecord(e0, stream);
+            cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream);
+            cudaEventRecord(e1, stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms > 0.f) {
+                total_ms += ms;
+                const double g = static_cast<double>(bytes) / (ms * 1e-3) * 1e-9;
+                best = g > best ? g : best;
+            }
+        }
+        if (cudaGetLastError() != cudaSuccess) status = PERTURB_GPU_ERR_CUDA;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (stream) cudaStreamDestroy(stream);
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (status != PERTURB_GPU_OK) return status;
+    *gbs_best = best;
+    if (gbs_mean != nullptr) {
+        *gbs_mean = total_ms > 0.0 ? static_cast<double>(bytes) * reps / (total_ms * 1e-3) * 1e-9 : 0.0;
+    }
     return PERTURB_GPU_OK;
 }

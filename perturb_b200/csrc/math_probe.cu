@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/perturb_gpu.h"
+#include "../../include/perturb_benchtools.h"
 #include "sgp4_math.cuh"
 
 namespace {

@@ -189,6 +189,85 @@ struct ResNodes {
     int k0, count;
 };
 
+// Kepler's equation as the reference solves it (src/sgp4.cpp:1965-1983): Newton iteration from
+// E = u, at most 10 corrections tem5, each clamped to +-0.95, stop after one smaller than 1e-12;
+// the sin/cos it keeps are those of the iterate BEFORE that last correction, which is never
+// applied to them.
+//
+// Three observations make this cheaper without leaving the reference's fixed point:
+//  * Newton converges quadratically, so once a correction d is below 6e-8 the NEXT one
+//    would be < e d^2 / (2 (1 - e)) < 1e-12: the reference's next pass only re-evaluates
+//    sin/cos at E + d and stops. That pass is replaced by rotating (sin E, cos E) by d
+//    (second-order series, error < 1e-22) after the loop.
+//  * a lane that has finished only stops moving its iterate: the later passes the rest of
+//    the warp needs recompute the very same sin/cos and correction from the frozen
+//    iterate (same instructions, same inputs), so nothing has to be saved or selected per
+//    pass, and a result never depends on how many iterations the other lanes of the warp
+//    (other times of the same satellite) need.
+//  * the clamp is two selects; a NaN correction stays NaN and stops the lane, as in the
+//    reference.
+template <bool UNIFORM>
+__device__ __forceinline__ void kepler_newton(double u, double axnl, double aynl, double &sineo1,
+                                              double &coseo1) {
+    double eo1 = u, tem5, mag;
+    bool done = false;
+    int ktr = 1;
+#pragma unroll 1
+    do {
+        sincos_cw(eo1, sineo1, coseo1);
+        tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
+        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
+        tem5 = (tem5 > kMc[MC_0P95]) ? kMc[MC_0P95] : tem5;
+        tem5 = (tem5 < -kMc[MC_0P95]) ? -kMc[MC_0P95] : tem5;
+        mag = fabs(tem5);
+        // stop as evaluated (< 1e-12), or stop with one confirming rotation owed (< 6e-8)
+        const bool stop = !(mag >= kMc[MC_1EM12]) || (mag < 5.9604644775390625e-8 && ktr < 10);
+        done = done || stop;
+        if (!done) eo1 = eo1 + tem5;
+        ++ktr;
+    } while (ktr <= 10 && !(UNIFORM ? __all_sync(0xffffffffu, done) : done));
+    // sin/cos at E + d for the lanes that owe the confirming pass (identity otherwise)
+    const double dfin = (done && mag >= kMc[MC_1EM12]) ? tem5 : 0.0;
+    const double h = dfin * dfin;
+    const double sd = __fma_rn(-0.16666666666666666 * h, dfin, dfin);
+    const double cd = __fma_rn(-0.5, h, 1.0);
+    const double s_rot = __fma_rn(coseo1, sd, sineo1 * cd);
+    const double c_rot = __fma_rn(-sineo1, sd, coseo1 * cd);
+    sineo1 = s_rot;
+    coseo1 = c_rot;
+}
+
+// Kepler's equation for a nearly circular orbit, e^2 = axnl^2 + aynl^2 < 4e-4. With E = u + d
+// the equation reads  d = g0 cos d + g1 sin d,  g0 = axnl sin u - aynl cos u,
+// g1 = axnl cos u + aynl sin u  (|g0|, |g1| <= e, so |d| <= e / (1 - e)). Its solution to
+// fourth order in e is  d4 = g0 ((1 + g1 + g1^2 + g1^3) - g0^2 (1/2 + 5/3 g1))  (|d - d4| <
+// 2 e^5 = 7e-9); one Newton step on F(d) = d - g0 cos d - g1 sin d from there, with short Taylor
+// sums for sin/cos of the small d (no range reduction, no quadrant logic) and 1 / F' = 1 / (1 -
+// w) as 1 + w + w^2 (|w| <= e: the step is below 7e-9, so the w^3 left out moves it by < 6e-14),
+// lands within 4e-15 of the root. (sin E, cos E) is (sin u, cos u) rotated by d: ONE general
+// sin/cos, where the Newton iteration from E = u needs two or three. The reference stops once
+// a correction is below 1e-12 without applying it, so its own E sits within 1e-12 of the same
+// root (7e-9 km at LEO): both agree to that, far inside the parity bar.
+__device__ __forceinline__ void kepler_small(double u, double axnl, double aynl, double &sineo1,
+                                             double &coseo1) {
+    double su, cu;
+    sincos_cw(u, su, cu);
+    const double g0 = msb2(axnl, su, aynl, cu);
+    const double g1 = mad2(axnl, cu, aynl, su);
+    const double a = __dadd_rn(__fma_rn(__fma_rn(g1, g1, g1), g1, g1), 1.0);  // 1 + g1 + g1^2 + g1^3
+    const double b = __fma_rn(g1, kMc[MC_5O3], kMc[MC_HALF]);
+    const double d = __dmul_rn(g0, __fma_rn(-__dmul_rn(g0, g0), b, a));
+    double sd, cd;
+    sincos_taylor<2, 3>(d, sd, cd);
+    const double f = __fma_rn(-g1, sd, __fma_rn(-g0, cd, d));   // F(d)
+    const double w = msb2(g1, cd, g0, sd);                      // F'(d) = 1 - w
+    const double step = __dmul_rn(-f, __dadd_rn(__fma_rn(w, w, w), 1.0));
+    const double s2 = __fma_rn(cd, step, sd);   // sin / cos of d + step, first order:
+    const double c2 = __fma_rn(-sd, step, cd);  // step^2 / 2 < 3e-17
+    sineo1 = mad2(su, c2, cu, s2);
+    coseo1 = msb2(cu, c2, su, s2);
+}
+
 // Returns the raw sgp4 error code (0, 1, 2, 3, 4, 6). out[0..2] = r [km], out[3..5] = v
 // [km/s] are written for codes 0 and 6 only, exactly like the reference.
 //
@@ -513,54 +592,34 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double xl = mp + argpp + nodep + temp * xlcof * axnl;
 
     const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
-    // Newton iteration of the reference (at most 10 corrections tem5, each clamped to +-0.95,
-    // stop after one smaller than 1e-12; the sin/cos it keeps are those of the iterate BEFORE
-    // that last correction, which is never applied to them).
-    //
-    // Three observations make this cheaper without leaving the reference's fixed point:
-    //  * Newton converges quadratically, so once a correction d is below 6e-8 the NEXT one
-    //    would be < e d^2 / (2 (1 - e)) < 1e-12: the reference's next pass only re-evaluates
-    //    sin/cos at E + d and stops. That pass is replaced by rotating (sin E, cos E) by d
-    //    (second-order series, error < 1e-22) after the loop.
-    //  * a lane that has finished only stops moving its iterate: the later passes the rest of
-    //    the warp needs recompute the very same sin/cos and correction from the frozen
-    //    iterate (same instructions, same inputs), so nothing has to be saved or selected per
-    //    pass, and a result never depends on how many iterations the other lanes of the warp
-    //    (other times of the same satellite) need.
-    //  * the clamp is two selects; a NaN correction stays NaN and stops the lane, as in the
-    //    reference.
-    double eo1 = u, sineo1, coseo1, tem5, mag;
-    bool done = false;
-    int ktr = 1;
-#pragma unroll 1
-    do {
-        sincos_cw(eo1, sineo1, coseo1);
-        tem5 = 1.0 - coseo1 * axnl - sineo1 * aynl;
-        tem5 = div_coarse(u - aynl * coseo1 + axnl * sineo1 - eo1, tem5);
-        tem5 = (tem5 > kMc[MC_0P95]) ? kMc[MC_0P95] : tem5;
-        tem5 = (tem5 < -kMc[MC_0P95]) ? -kMc[MC_0P95] : tem5;
-        mag = fabs(tem5);
-        // stop as evaluated (< 1e-12), or stop with one confirming rotation owed (< 6e-8)
-        const bool stop = !(mag >= kMc[MC_1EM12]) || (mag < 5.9604644775390625e-8 && ktr < 10);
-        done = done || stop;
-        if (!done) eo1 = eo1 + tem5;
-        ++ktr;
-    } while (ktr <= 10 && !(UNIFORM ? __all_sync(0xffffffffu, done) : done));
-    {   // sin/cos at E + d for the lanes that owe the confirming pass (identity otherwise)
-        const double dfin = (done && mag >= kMc[MC_1EM12]) ? tem5 : 0.0;
-        const double h = dfin * dfin;
-        const double sd = __fma_rn(-0.16666666666666666 * h, dfin, dfin);
-        const double cd = __fma_rn(-0.5, h, 1.0);
-        const double s_rot = __fma_rn(coseo1, sd, sineo1 * cd);
-        const double c_rot = __fma_rn(-sineo1, sd, coseo1 * cd);
-        sineo1 = s_rot;
-        coseo1 = c_rot;
+    const double el2 = mad2(axnl, axnl, aynl, aynl);
+    // Kepler's equation  E = u - aynl cos E + axnl sin E  (src/sgp4.cpp:1965-1983). Nearly
+    // circular orbits (el2 < 4e-4, i.e. e < 0.02: most of any catalogue) are solved for
+    // delta = E - u in closed form, one general sin/cos instead of two or three (kepler_small);
+    // everything else runs the reference's Newton iteration (kepler_newton). The choice is made
+    // per lane from the lane's own el2 -- a result never depends on the other lanes of the warp
+    // -- while the branches are taken on warp votes, so control flow stays warp-uniform.
+    double sineo1, coseo1;
+    if (UNIFORM) {
+        const bool small = el2 < kMc[MC_KEPLER_SMALL];
+        if (__all_sync(0xffffffffu, small)) {
+            kepler_small(u, axnl, aynl, sineo1, coseo1);
+        } else {
+            kepler_newton<true>(u, axnl, aynl, sineo1, coseo1);
+            if (__any_sync(0xffffffffu, small)) {
+                double sf, cf;
+                kepler_small(u, axnl, aynl, sf, cf);
+                sineo1 = small ? sf : sineo1;
+                coseo1 = small ? cf : coseo1;
+            }
+        }
+    } else {
+        kepler_newton<false>(u, axnl, aynl, sineo1, coseo1);
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
     const double ecose = mad2(axnl, coseo1, aynl, sineo1);
     const double esine = msb2(axnl, sineo1, aynl, coseo1);
-    const double el2 = mad2(axnl, axnl, aynl, aynl);
     const double pl = am * (1.0 - el2);
     PB_FAIL_IF(pl < 0.0, 4);  // :1990
 

@@ -62,6 +62,7 @@ enum {
     MC_A0, MC_A1, MC_A2, MC_A3, MC_A4, MC_A5, MC_A6, MC_A7,
     // (1 + x)^(-2/3) = 1 + x (B1 + x (B2 + ...)): binomial coefficients -2/3, 5/9, -40/81, ...
     MC_B1, MC_B2, MC_B3, MC_B4, MC_B5, MC_B6,
+    MC_KEPLER_SMALL, MC_5O3,  // kepler_small: its e^2 bound, 5/3
     MC_COUNT
 };
 
@@ -97,6 +98,7 @@ static __constant__ double kMc[MC_COUNT] = {
     -6.55414157038025635416e-02, 4.72544858625266947505e-02,
     -6.66666666666666629659e-01, 5.55555555555555580227e-01, -4.93827160493827133081e-01,
     4.52674897119341557161e-01, -4.22496570644718794085e-01, 3.99024538942234441308e-01,
+    4.0e-4, 1.66666666666666674068e+00,
 };
 
 // ---- reciprocal, division, square root ---------------------------------------------------

@@ -46,6 +46,15 @@ constexpr int kThreads = kWarps * 32;
 #endif
 constexpr int kTpl = PB_TPL;                   // times per lane (1 or 2)
 constexpr int kTimeTile = kThreads * kTpl;     // times per CTA
+// PB_TPL = 2 comes in two forms. Rolled (default): lane l owns times l and l + 32 of the warp's
+// 64, one copy of the body. PB_TPL_PAIR: lane l owns the ADJACENT times 2l and 2l + 1, the two
+// evaluations are unrolled into one instruction stream (constants, addresses and loop control
+// shared, two independent dependency chains) and the state planes are written with 16-byte
+// stores, 512 contiguous bytes per warp and plane.
+#ifndef PB_TPL_PAIR
+#define PB_TPL_PAIR 0
+#endif
+constexpr bool kPair = (PB_TPL_PAIR != 0) && (kTpl == 2);
 
 template <int CLS>
 struct TileFields {
@@ -92,6 +101,7 @@ struct PropParams {
     int chunks;
     GravConsts g;
     int opsmode_a;
+    int vec_ok;  // state planes and error rows allow 16-byte / 8-byte paired stores (kPair)
     // resonance node table (deep-space resonant classes only)
     const ResNode *res_nodes;  // [resonant slot][res_cap] node records
     const int *res_k0;         // [resonant slots] first tabulated step index
@@ -245,37 +255,48 @@ __device__ __forceinline__ void merge_summary(LaneSummary &a, const LaneSummary 
 // every 4th (2nd) satellite -- instead of leaving warps idle and the rest with all 32
 // satellites to walk one after the other. A separate instantiation: the variable loop bounds
 // cost the long-grid kernel registers (16 bytes of spills, 9 % slower when tried in place).
-template <int CLS, int MODE, bool SPLIT = false>
+//
+// SATS: satellites of the 32-satellite tile one CTA walks (32, 16 or 8). All CTAs of a launch
+// take the same time, so the last, partly filled wave leaves SMs idle for up to one CTA
+// duration: on a grid of few waves (30 000 satellites x 1440 times = 10.6 waves of 32-satellite
+// CTAs) smaller CTAs shorten that tail for a slightly larger staging share.
+template <int CLS, int MODE, bool SPLIT = false, int SATS = PB_TILE_SATS>
 __global__ void __launch_bounds__(kThreads, (CLS <= PB_CLS_NEAR_SIMP) ? PB_MIN_BLOCKS_NEAR
                                            : (CLS == PB_CLS_DEEP_R2) ? PB_MIN_BLOCKS_R2
                                                                      : PB_MIN_BLOCKS_DEEP)
 sgp4_prop_kernel(const PropParams p) {
+    static_assert(SATS == 32 || SATS == 16 || SATS == 8, "CTA walks 32, 16 or 8 satellites");
+    constexpr int kSub = PB_TILE_SATS / SATS;  // CTAs per (satellite tile, time tile)
     constexpr bool WANT_ELEMENTS = (MODE == kModeElements);
     using TF = TileFields<CLS>;
     constexpr int kRowsPad = (TF::kRows + 1) & ~1;  // even: every satellite's block 16 B aligned
-    __shared__ __align__(16) double s_pf[kRowsPad * PB_TILE_SATS];
+    __shared__ __align__(16) double s_pf[kRowsPad * SATS];
     __shared__ double s_ta[kTimeTile];
     __shared__ double s_tb[kTimeTile];
-    __shared__ int s_perm[PB_TILE_SATS];
+    __shared__ int s_perm[SATS];
     constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
-    __shared__ int4 s_res[kResonant ? PB_TILE_SATS : 1];  // {k0, count, first record, -}
+    __shared__ int4 s_res[kResonant ? SATS : 1];  // {k0, count, first record, -}
 
     const int ttile = blockIdx.x % p.n_time_tiles;
-    const int stile = p.tile_begin + blockIdx.x / p.n_time_tiles;
+    const int stile_sub = blockIdx.x / p.n_time_tiles;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const size_t sat0 = static_cast<size_t>(stile) * PB_TILE_SATS;
+    const size_t sat0 = static_cast<size_t>(p.tile_begin) * PB_TILE_SATS +
+                        static_cast<size_t>(stile_sub) * SATS;
 
     // ---- stage constants (coalesced 256 B rows) and this CTA's slice of the time grid ----
     // (a grid that fits one time tile is launched with just the warps it fills: blockDim.x
     // may be below kThreads, so the staging loops go by the actual CTA size)
     const int n_warps = static_cast<int>(blockDim.x >> 5);
-    for (int r = warp; r < TF::kRows; r += n_warps) {
-        const int f = r < TF::kEndA ? r : r - TF::kEndA + TF::kBeginB;
-        s_pf[lane * kRowsPad + r] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + lane];
+    {   // a warp covers kSub rows of SATS satellites per pass
+        const int sl = lane % SATS, rl = lane / SATS;
+        for (int r = warp * kSub + rl; r < TF::kRows; r += n_warps * kSub) {
+            const int f = r < TF::kEndA ? r : r - TF::kEndA + TF::kBeginB;
+            s_pf[sl * kRowsPad + r] = p.pf[static_cast<size_t>(f) * p.n_pad + sat0 + sl];
+        }
     }
-    if (threadIdx.x < PB_TILE_SATS) s_perm[threadIdx.x] = p.perm[sat0 + threadIdx.x];
-    if (kResonant && threadIdx.x < PB_TILE_SATS) {
+    if (threadIdx.x < SATS) s_perm[threadIdx.x] = p.perm[sat0 + threadIdx.x];
+    if (kResonant && threadIdx.x < SATS) {
         const size_t rs = sat0 + threadIdx.x - p.res_first_slot;
         const bool have = p.res_nodes != nullptr;
         s_res[threadIdx.x] = make_int4(have ? p.res_k0[rs] : 0, have ? p.res_cnt[rs] : 0,
@@ -301,7 +322,8 @@ sgp4_prop_kernel(const PropParams p) {
         sat_first = warp / groups;
         sat_step = kWarps / groups;
     }
-    const int i0 = tgroup * (32 * kTpl) + lane;
+    const int i0 = tgroup * (32 * kTpl) + (kPair ? 2 * lane : lane);
+    constexpr int kTimeStep = kPair ? 1 : 32;  // distance between a lane's two times
     if (k_base + tgroup * 32 * kTpl >= p.m) return;  // whole warp beyond the grid
     // (With PB_TPL = 2, skipping the second group of 32 times when only it lies beyond the grid
     // was measured: a data-dependent trip count makes ptxas treat the body as divergent, +1.4 %
@@ -309,14 +331,14 @@ sgp4_prop_kernel(const PropParams p) {
     double ta[kTpl], tb[kTpl];
 #pragma unroll
     for (int j = 0; j < kTpl; ++j) {
-        ta[j] = s_ta[i0 + 32 * j];
-        tb[j] = s_tb[i0 + 32 * j];
+        ta[j] = s_ta[i0 + kTimeStep * j];
+        tb[j] = s_tb[i0 + kTimeStep * j];
     }
     const ClassFlags no_flags = {false, false, 0};
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
 #pragma unroll 1
-    for (int s = SPLIT ? sat_first : 0; s < PB_TILE_SATS; s += SPLIT ? sat_step : 1) {
+    for (int s = SPLIT ? sat_first : 0; s < SATS; s += SPLIT ? sat_step : 1) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
         const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
@@ -335,8 +357,47 @@ sgp4_prop_kernel(const PropParams p) {
         LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
                            __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
 
-        // With PB_TPL = 2 the two evaluations share ONE copy of the code (a rolled loop): the body is ~15 KB
-        // of SASS and the instruction cache is 32 KB.
+        if (kPair && MODE == kModeStates) {
+            // both evaluations in one instruction stream, then paired stores
+            double r[2][6];
+            int cd[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double t = tsince_of(p.use_jd, ta[j], tb[j], k(PF_JD0), k(PF_JDF0));
+                cd[j] = sgp4_eval<CLS, false, true>(k, p.g, p.opsmode_a != 0, no_flags, t, r[j],
+                                                    nullptr, kResonant ? &nodes : nullptr);
+            }
+            const int kt = k_base + i0;
+            const bool w0 = (cd[0] == 0) || (cd[0] == 6), w1 = (cd[1] == 0) || (cd[1] == 6);
+            if (!__all_sync(0xffffffffu, w0 && w1)) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    r[0][c] = w0 ? r[0][c] : nan;
+                    r[1][c] = w1 ? r[1][c] : nan;
+                }
+            }
+            if (p.vec_ok && kt + 1 < p.m) {
+                double *q = row + kt;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    *reinterpret_cast<double2 *>(q) = make_double2(r[0][c], r[1][c]);
+                    q += p.plane_stride;
+                }
+                *reinterpret_cast<int2 *>(erow + kt) = make_int2(cd[0], cd[1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (kt + j < p.m) {
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) row[c * p.plane_stride + kt + j] = r[j][c];
+                        erow[kt + j] = cd[j];
+                    }
+                }
+            }
+            continue;
+        }
+        // With PB_TPL = 2 (rolled) the two evaluations share ONE copy of the code: the body is
+        // ~15 KB of SASS and the instruction cache is 32 KB.
 #pragma unroll 1
         for (int j = 0; j < kTpl; ++j) {
             const double t = tsince_of(p.use_jd, (j == 0) ? ta[0] : ta[kTpl - 1], (j == 0) ? tb[0] : tb[kTpl - 1],
@@ -346,7 +407,7 @@ sgp4_prop_kernel(const PropParams p) {
             const int cd = sgp4_eval<CLS, WANT_ELEMENTS, true>(
                 k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
                 kResonant ? &nodes : nullptr);
-            const int kt = k_base + i0 + 32 * j;
+            const int kt = k_base + i0 + kTimeStep * j;
             // every lane of the warp is here (uniform control flow): one vote decides whether
             // the stores need the NaN selects at all
             const bool all_written = __all_sync(0xffffffffu, (cd == 0) || (cd == 6));
@@ -607,10 +668,13 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
     const long long blocks = static_cast<long long>(tiles) * p.n_time_tiles;
     // grid.x limit is 2^31-1; at 1M satellites x 10k times this is 31250 * 40 blocks.
     cudaStream_t stream = main;
-    const bool forked = (launches > 0) && l.aux[CLS] != nullptr && l.fork != nullptr;
+    const bool forked = (launches > 0) && l.aux[CLS] != nullptr && l.fork != nullptr &&
+                        l.fork_recorded;
     if (forked) {
         stream = l.aux[CLS];
-        cudaStreamWaitEvent(stream, l.fork, 0);
+        if (cudaStreamWaitEvent(stream, l.fork, 0) != cudaSuccess) {
+            stream = main;  // could not fork: run this class in line
+        }
     }
     if (p.m <= kShortGrid) {
         const unsigned sb = static_cast<unsigned>((tiles + kWarps - 1) / kWarps);
@@ -642,19 +706,42 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
             } else {
                 sgp4_prop_kernel<CLS, kModeStates, true><<<nb, kThreads, 0, stream>>>(p);
             }
-        } else if (p.partials != nullptr) {
-            sgp4_prop_kernel<CLS, kModeSummary><<<nb, threads, 0, stream>>>(p);
-        } else if (p.states != nullptr) {
-            sgp4_prop_kernel<CLS, kModeRecords><<<nb, threads, 0, stream>>>(p);
-        } else if (p.elements != nullptr) {
-            sgp4_prop_kernel<CLS, kModeElements><<<nb, threads, 0, stream>>>(p);
         } else {
-            sgp4_prop_kernel<CLS, kModeStates><<<nb, threads, 0, stream>>>(p);
+            // CTA size in satellites: 32 when the launch is many waves long anyway, else 16 / 8
+            int sats = l.cta_sats;
+            if (sats != 32 && sats != 16 && sats != 8) {
+                const long long per_wave = 148LL * 6;  // SMs x resident CTAs, roughly
+                sats = (blocks >= 40 * per_wave) ? 32 : (blocks >= 20 * per_wave) ? 16 : 8;
+            }
+            if (p.n_time_tiles == 1 || blocks * 4 > 0x7fffffffLL) sats = 32;
+            const unsigned nbs = static_cast<unsigned>(blocks * (PB_TILE_SATS / sats));
+#define PB_LAUNCH_MODE(MODE_)                                                                   \
+    do {                                                                                        \
+        if (sats == 32) {                                                                       \
+            sgp4_prop_kernel<CLS, MODE_, false, 32><<<nbs, threads, 0, stream>>>(p);            \
+        } else if (sats == 16) {                                                                \
+            sgp4_prop_kernel<CLS, MODE_, false, 16><<<nbs, threads, 0, stream>>>(p);            \
+        } else {                                                                                \
+            sgp4_prop_kernel<CLS, MODE_, false, 8><<<nbs, threads, 0, stream>>>(p);             \
+        }                                                                                       \
+    } while (0)
+            if (p.partials != nullptr) {
+                PB_LAUNCH_MODE(kModeSummary);
+            } else if (p.states != nullptr) {
+                PB_LAUNCH_MODE(kModeRecords);
+            } else if (p.elements != nullptr) {
+                PB_LAUNCH_MODE(kModeElements);
+            } else {
+                PB_LAUNCH_MODE(kModeStates);
+            }
+#undef PB_LAUNCH_MODE
         }
     }
-    if (forked) {
-        cudaEventRecord(l.join[CLS], stream);
-        cudaStreamWaitEvent(main, l.join[CLS], 0);
+    if (stream != main) {
+        // a failure here is sticky and surfaces in the caller's cudaGetLastError()
+        if (cudaEventRecord(l.join[CLS], stream) == cudaSuccess) {
+            cudaStreamWaitEvent(main, l.join[CLS], 0);
+        }
     }
     ++launches;
 }
@@ -693,6 +780,11 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.g.vkmpersec = l.radiusearthkm * l.xke / 60.0;
     p.g.inv_xke = 1.0 / l.xke;
     p.opsmode_a = l.opsmode_a;
+    p.vec_ok = (l.out != nullptr && (reinterpret_cast<uintptr_t>(l.out) & 15u) == 0 &&
+                (reinterpret_cast<uintptr_t>(l.err) & 7u) == 0 && l.row_stride % 2 == 0 &&
+                l.plane_stride % 2 == 0 && l.err_row_stride % 2 == 0)
+                   ? 1
+                   : 0;
     int launches = 0;
     p.res_nodes = nullptr;
     p.res_k0 = p.res_cnt = nullptr;
@@ -716,13 +808,18 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     }
     const int prelaunches = launches;
     launches = 0;
-    if (l.fork != nullptr) cudaEventRecord(l.fork, stream);
+    // grid.x is limited to 2^31 - 1 CTAs (a CTA may cover as few as 8 satellites x 128 times)
+    for (int c = 0; c < PB_CLS_COUNT; ++c) {
+        if (static_cast<long long>(l.tile_count[c]) * p.n_time_tiles > 0x7fffffffLL) return -1;
+    }
+    PropLaunch lf = l;
+    lf.fork_recorded = (l.fork != nullptr) && cudaEventRecord(l.fork, stream) == cudaSuccess;
     // most expensive per evaluation first
-    launch_class<PB_CLS_DEEP_R2>(l, p, stream, launches);
-    launch_class<PB_CLS_DEEP_R1>(l, p, stream, launches);
-    launch_class<PB_CLS_DEEP_NR>(l, p, stream, launches);
-    launch_class<PB_CLS_NEAR_FULL>(l, p, stream, launches);
-    launch_class<PB_CLS_NEAR_SIMP>(l, p, stream, launches);
+    launch_class<PB_CLS_DEEP_R2>(lf, p, stream, launches);
+    launch_class<PB_CLS_DEEP_R1>(lf, p, stream, launches);
+    launch_class<PB_CLS_DEEP_NR>(lf, p, stream, launches);
+    launch_class<PB_CLS_NEAR_FULL>(lf, p, stream, launches);
+    launch_class<PB_CLS_NEAR_SIMP>(lf, p, stream, launches);
     if (l.summary_partials != nullptr && l.summary_out != nullptr && l.n > 0) {
         // every (satellite, chunk) partial with chunk * 32 * kTpl < m has been written by exactly one
         // warp of exactly one class launch; all of them were joined back into `stream`

@@ -16,7 +16,7 @@ cp -r "$root/perturb_b200/csrc" "$work/perturb_b200/"
 cp -r "$root/include/." "$work/include/"
 cd "$work/perturb_b200/csrc"
 rm -f *.o
-make OUT="$root/perturb_b200/variants/$name.so" "$@" > build.log 2>&1 || { tail -20 build.log; exit 1; }
+make product OUT="$root/perturb_b200/variants/$name.so" "$@" > build.log 2>&1 || { tail -20 build.log; exit 1; }
 echo "$name: $(grep -c 'spill stores' sgp4_prop.ptxas.log) kernels;" \
      "near-Earth states kernel: $(grep -A2 'sgp4_prop_kernelILi0ELi0ELb0' sgp4_prop.ptxas.log | grep -o 'Used [0-9]* registers' | head -1)"
 rm -rf "$work"

@@ -22,7 +22,8 @@ def _compile(tmp_path, extra=(), src=SRC, name="iss_example"):
     exe = str(tmp_path / name)
     libdir = os.path.dirname(capi.LIB_PATH)
     cmd = ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
-           *extra, src, "-o", exe, "-L" + libdir, "-lperturb_gpu", "-Wl,-rpath," + libdir]
+           *extra, src, "-o", exe, "-L" + libdir, "-lperturb_gpu", "-lperturb_benchtools",
+           "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
     return exe
 

@@ -16,7 +16,7 @@ def probe(fn, x, y=None):
     y = np.ascontiguousarray(np.ones_like(x) if y is None else y, dtype=np.float64)
     out = np.empty_like(x)
     dp = C.POINTER(C.c_double)
-    st = capi.lib().perturb_gpu_math_probe(
+    st = capi.tools().perturb_gpu_math_probe(
         fn, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size)
     capi.check(st, "perturb_gpu_math_probe")
     return out

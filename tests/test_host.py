@@ -23,7 +23,7 @@ def _declared_functions(header):
 
 
 def test_library_exports_every_declared_symbol():
-    declared = _declared_functions("perturb_gpu.h") + _declared_functions("perturb_synth.h")
+    declared = _declared_functions("perturb_gpu.h")
     assert len(declared) >= 19
     lib = C.CDLL(capi.LIB_PATH)
     for name in declared:
@@ -32,6 +32,19 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH]).decode()
     exported = set(re.findall(r" T (perturb_\w+)", out))
     assert set(declared) <= exported
+    # the product carries no bench / test hooks: those live in libperturb_benchtools.so
+    assert not (exported & set(capi.TOOLS_EXPORTS)), exported & set(capi.TOOLS_EXPORTS)
+
+
+def test_benchtools_library_exports_its_header_and_is_not_the_product():
+    declared = sorted(set(_declared_functions("perturb_benchtools.h") + _declared_functions("perturb_synth.h")))
+    assert declared == sorted(capi.TOOLS_EXPORTS)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.TOOLS_PATH]).decode()
+    exported = set(re.findall(r" T (perturb_\w+)", out))
+    assert set(declared) <= exported
+    assert not (exported & set(capi.EXPORTS))
+    needed = subprocess.check_output(["readelf", "-d", capi.TOOLS_PATH]).decode()
+    assert "libperturb_gpu" not in needed
 
 
 def test_library_is_sm100a_and_has_both_kernels():
@@ -188,6 +201,7 @@ def test_abi_headers_are_plain_c99(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     src = tmp_path / "abi.c"
-    src.write_text('#include "perturb_gpu.h"\n#include "perturb_synth.h"\nint main(void) { return 0; }\n')
+    src.write_text('#include "perturb_gpu.h"\n#include "perturb_synth.h"\n#include "perturb_benchtools.h"\n'
+                   'int main(void) { return 0; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only",
                            "-I" + os.path.join(ROOT, "include"), str(src)])
