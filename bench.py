@@ -15,11 +15,19 @@ Prints ONE JSON line (rank 0). Keys beyond the base contract:
   roofline_hbm  the second roofline: 52 B written per evaluation against MEASURED_PEAKS.json.
   cpu_baseline  the reference's scalar loop (oracle/_ref, else the C port) on the host cores.
   e2e           the same metric through the C ABI with HOST buffers (H2D of the time grid and
-                D2H of all states and error codes inside the timed region).
+                D2H of all states and error codes inside the timed region), with the raw D2H
+                ceiling of the box measured in the same run (d2h_ceiling_gbs, frac_of_ceiling).
+  e2e_dropin    the drop-in call itself, perturb::SatelliteBatch::propagate into a
+                std::vector<StateVector> (tests/cpp/dropin_bench.cpp, a C++ program).
+  workloads     BASELINE.json configs 3, 4, 5 at full size (device-resident), each with its own
+                clocks and FP64-pipe share; c5_strong at N > 1 (1 M satellites / N per GPU).
+  inproc_sharded  (N > 1, rank 0) one process driving all N GPUs: ShardedSatelliteBatch,
+                bit-identity against the unsharded batch, device-resident gather over NVLink.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -153,19 +161,37 @@ def bind_to_gpu_numa_node(index):
         return "numa: unbound (%s)" % type(exc).__name__
 
 
-def catalogue_lines(workload, rank, world):
-    """Global catalogue of world x n satellites, this rank's satellite range."""
+def catalogue_lines(workload, rank, world, total=None):
+    """Global catalogue of world x n satellites (or `total`), this rank's satellite range."""
     import perturb_b200 as pb
     cfg, n, m = WORKLOADS[workload]
-    total = n * world
+    total = n * world if total is None else total
     b1, b2 = pb.synth_catalog(cfg, total)
     s1, s2, n_local = pb.shard_blocks(b1, b2, total, rank, world)
-    assert n_local == n
-    return s1, s2, n, m
+    return s1, s2, n_local, m
+
+
+def config_of(workload, n, m, world=1, cls=None):
+    """The `config` object of a bench line: identical keys in the GPU arm and the reference arm."""
+    cfg = {
+        "workload": WORKLOAD_TEXT[workload],
+        "satellites_per_gpu": n, "times": m, "evals_per_step": float(n) * m * world,
+        "sharding": "satellite ranges, one process per GPU, no data-path collective",
+        "l2": "256 MiB buffer rewritten between timed iterations (outside the event pair); "
+              "each step also writes %.2f GB of outputs" % (float(n) * m * 52 / 1e9),
+        "outputs": "device-resident SoA planes [6][n][m] f64 + err [n][m] i32",
+    }
+    if cls is not None:
+        cfg["orbit_classes"] = {"near_full": int(cls[0]), "near_simplified": int(cls[1]),
+                                "deep_nonresonant": int(cls[2]), "deep_24h": int(cls[3]),
+                                "deep_12h": int(cls[4])}
+    return cfg
 
 
 def cpu_arm(workload, steps, warmup, cores=None, budget_s=12.0):
-    """The reference's scalar loop on all host cores over a bounded sample of the workload."""
+    """The reference's scalar loop on all host cores over a bounded sample of the workload.
+    Touches only libperturb_benchtools.so (catalogue text, time grid) and oracle/ -- never the
+    product library."""
     import perturb_b200 as pb
     from oracle import port, ref
     cfg, n, m = WORKLOADS[workload]
@@ -224,13 +250,204 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.workload], "satellites_per_gpu": n, "times": m},
+        "config": config_of(args.workload, n, m, max(1, args.gpus)),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def load_profile_counts():
+    """FP64 instructions per evaluation of each class kernel as counted by ncu (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        return {}
+
+
+def fp64_pipe_share(prof, cls, m, launch_ms, sm_mhz):
+    """Share of the FP64 pipe's issue cycles (2 warp instructions per clock per SM) a step keeps
+    busy, from the per-class FP64 instruction counts -- the executed-work roofline view."""
+    ipe = prof.get("fp64_instr_per_eval")
+    if not ipe or not sm_mhz:
+        return None
+    instr = float(sum(ipe[c] * cls[c] for c in range(5))) * m / 32.0
+    cap = launch_ms * 1e-3 * sm_mhz * 1e6 * N_SM * 2.0
+    return {"fp64_warp_instr_per_step": instr, "frac_of_fp64_issue_cycles": instr / cap,
+            "fp64_instr_per_eval": ipe, "source": prof.get("_fp64_instr_source")}
+
+
+def time_device_resident(pb, torch, batch, n, m, dev, local, steps, warmup, dist, chunk=None):
+    """K timed steps of the hot path with device-resident outputs: CUDA events on the launching
+    stream around each step, L2 flushed between steps (outside the event pair), NVML clock
+    sampling during the region. A step covers the whole time grid; with `chunk` it is walked in
+    time-chunks of that many steps into one reused output buffer (grids whose 52 B/evaluation
+    exceed the GPU's memory). Returns per-step ms (this rank), clocks, launches per step."""
+    jd, fr = pb.synth_time_grid(m)
+    d_jd = torch.tensor(jd, device=dev)
+    d_fr = torch.tensor(fr, device=dev)
+    mc = m if chunk is None else min(m, chunk)
+    out = torch.empty((6, n, mc), dtype=torch.float64, device=dev)
+    err = torch.empty((n, mc), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    launches = [0]
+
+    def step():
+        launches[0] = 0
+        for k0 in range(0, m, mc):
+            mk = min(mc, m - k0)
+            batch.propagate(d_jd[k0:k0 + mk], d_fr[k0:k0 + mk], out[:, :, :mk], err[:, :mk],
+                            stream=sp, sync=False)
+            launches[0] += batch.last_launch_count()
+
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    # keep the GPU under the same load a little longer if the region was too short to sample
+    while len(sampler.samples) < 5 and time.perf_counter() - wall0 < 3.0:
+        step()
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    if dist is not None:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ok_fraction = float((err == 0).double().mean())
+    del out, err, flush
+    torch.cuda.empty_cache()
+    return {"step_ms": step_ms, "clocks": clocks, "launches": launches[0], "wall": wall,
+            "ok_fraction": ok_fraction, "chunk": mc}
+
+
+def extra_workload(pb, torch, name, rank, world, local, dev, dist, fp64_peak, prof, steps,
+                   total=None, chunk_bytes=60e9):
+    """One more BASELINE config, device-resident, on this rank's shard; returns its record (on
+    every rank; values are whole-job, max over ranks)."""
+    b1, b2, n, m = catalogue_lines(name, rank, world, total)
+    batch = pb.SatelliteBatch.from_text(b1, b2, pb.WGS72, "i", device=local, n=n)
+    cls = np.bincount(batch.orbit_class(), minlength=5)
+    chunk = None
+    if float(n) * m * BYTES_PER_EVAL > chunk_bytes:
+        chunk = max(128, int(chunk_bytes / (float(n) * BYTES_PER_EVAL)) // 128 * 128)
+    r = time_device_resident(pb, torch, batch, n, m, dev, local, steps, 3, dist, chunk)
+    batch.close()
+    total_ms = float(sum(r["step_ms"]))
+    max_ms = pb.max_over_ranks(total_ms, dist, dev)
+    n_all = n * world if total is None else total
+    value = float(n_all) * m * steps / (max_ms * 1e-3)
+    launch_ms = total_ms / steps
+    falg = float(sum(F_ALG[c] * cls[c] for c in range(5)) / max(1, cls.sum()))
+    tfl = falg * float(n) * m / (launch_ms * 1e-3) * 1e-12
+    return {
+        "workload": WORKLOAD_TEXT[name], "satellites_per_gpu": n, "satellites": n_all, "times": m,
+        "value": value, "unit": "evals/s", "ms_per_step": max_ms / steps, "steps": steps,
+        "time_chunk": r["chunk"], "launches_per_step": r["launches"],
+        "classes": cls.tolist(), "tflops_v0": tfl,
+        "frac_of_fp64_peak_v0": tfl / fp64_peak if fp64_peak > 0 else None,
+        "fp64_pipe": fp64_pipe_share(prof, cls, m, launch_ms, r["clocks"].get("sm_mhz")),
+        "hbm_gbs": BYTES_PER_EVAL * float(n) * m / (launch_ms * 1e-3) * 1e-9,
+        "clocks": r["clocks"], "ok_fraction": r["ok_fraction"],
+    }
+
+
+def nvlink_rx_kib(index):
+    """Total NVLink data received by GPU `index` so far (KiB, all links), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        v = pynvml.nvmlDeviceGetFieldValues(
+            h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])[0]
+        if v.nvmlReturn != 0:
+            return None
+        return int(v.value.ullVal)
+    except Exception:
+        return None
+
+
+def inproc_sharded(pb, torch, workload, world, steps):
+    """(rank 0, N > 1) ONE process drives all N GPUs: ShardedSatelliteBatch over the same global
+    catalogue, bit-identity against the unsharded batch, and the device-resident gather (every
+    shard's kernel 2 stores its rows into GPU 0 over NVLink peer access), with the NVLink
+    receive counter of GPU 0 read around it."""
+    cfg, n, m = WORKLOADS[workload]
+    total = n * world
+    b1, b2 = pb.synth_catalog(cfg, total)
+    tles, _ = pb.parse_tle_blocks(b1, b2, total, flavor=1)
+    jd, fr = pb.synth_time_grid(m)
+    dev0 = torch.device("cuda", 0)
+    whole = pb.SatelliteBatch.from_parsed(tles, pb.WGS72, "i", device=0)
+    ref_out = torch.empty((6, total, m), dtype=torch.float64, device=dev0)
+    ref_err = torch.empty((total, m), dtype=torch.int32, device=dev0)
+    d_jd, d_fr = torch.tensor(jd, device=dev0), torch.tensor(fr, device=dev0)
+    torch.cuda.synchronize(dev0)
+    whole.propagate(d_jd, d_fr, ref_out, ref_err)
+    whole.close()
+    sharded = pb.ShardedSatelliteBatch.from_parsed(tles, list(range(world)), pb.WGS72, "i")
+    out, err = sharded.propagate_to_device(jd, fr, device=0)  # warm-up: enables peer access
+    same = bool(torch.equal(out.view(torch.int64), ref_out.view(torch.int64)) and
+                torch.equal(err, ref_err))
+    del ref_out, ref_err
+    for d in range(world):
+        torch.cuda.synchronize(torch.device("cuda", d))
+    rx0 = nvlink_rx_kib(0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sharded.propagate(jd, fr, out, err)  # enqueue on every device, then synchronise all
+    secs = (time.perf_counter() - t0) / steps
+    rx1 = nvlink_rx_kib(0)
+    remote = sum(hi - lo for (lo, hi) in sharded.ranges[1:])
+    remote_bytes = float(remote) * m * BYTES_PER_EVAL
+    rec = {
+        "devices": world, "satellites": total, "times": m, "bit_identical": same,
+        "ranges": [list(r) for r in sharded.ranges],
+        "evals_per_s_gathered": float(total) * m / secs, "ms_per_step": secs * 1e3, "steps": steps,
+        "gather_gbs_into_target": remote_bytes / secs * 1e-9,
+        "remote_bytes_per_step_expected": remote_bytes,
+        "nvlink_rx_bytes_per_step_gpu0": None if rx0 is None or rx1 is None
+        else (rx1 - rx0) * 1024.0 / steps,
+        "what": "one process, %d GPUs: every shard's kernel 2 stores its rows straight into "
+                "GPU 0 (NVLink peer access); wall clock around enqueue-all + synchronise-all" % world,
+    }
+    for b in sharded.batches:
+        b.close()
+    return rec
+
+
+def dropin_harness(workload, local, steps):
+    """perturb::SatelliteBatch::propagate into a std::vector<StateVector>: the C++ harness
+    (tests/cpp/dropin_bench.cpp, prebuilt by __graft_entry__.build(); compiled here if absent)."""
+    import __graft_entry__ as ge
+    exe = ge.DROPIN_BENCH
+    if not os.path.exists(exe):
+        ge.build_dropin_bench()
+    cfg, n, m = WORKLOADS[workload]
+    me = min(m, E2E_MAX_TIMES)
+    out = subprocess.run([exe, str(cfg), str(n), str(me), str(steps), str(local)],
+                         capture_output=True, text=True, timeout=600)
+    line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else "{}"
+    rec = json.loads(line)
+    if out.returncode != 0 or "error" in rec:
+        raise RuntimeError("dropin_bench failed (%d): %s %s" % (out.returncode, line, out.stderr[-300:]))
+    return rec
 
 
 def run_gpu(args):
@@ -264,52 +481,14 @@ def run_gpu(args):
     cls = np.bincount(batch.orbit_class(), minlength=5)
     falg = float(sum(F_ALG[c] * cls[c] for c in range(5)) / max(1, cls.sum()))
 
-    jd, fr = pb.synth_time_grid(m)
-    d_jd = torch.tensor(jd, device=dev)
-    d_fr = torch.tensor(fr, device=dev)
-    out = torch.empty((6, n, m), dtype=torch.float64, device=dev)
-    err = torch.empty((n, m), dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
-    sp = stream.cuda_stream
-
     peak = pb.capi.C.c_double(0.0)
     if pb.capi.tools().perturb_gpu_measure_fp64_peak(local, pb.capi.C.byref(peak)) != 0:
         raise SystemExit("bench.py: perturb_gpu_measure_fp64_peak failed")
     fp64_peak = peak.value
 
-    def step():
-        batch.propagate(d_jd, d_fr, out, err, stream=sp, sync=False)
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize(dev)
-    launches_per_step = batch.last_launch_count()
-
     # ---- device-resident timing: K steps, CUDA events on the launching stream ----
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local)
-    sampler.start()
-    wall0 = time.perf_counter()
-    for a, b in evs:
-        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
-        a.record(stream)
-        step()
-        b.record(stream)
-    torch.cuda.synchronize(dev)
-    wall = time.perf_counter() - wall0
-    # keep the GPU under the same load a little longer if the region was too short to sample
-    while len(sampler.samples) < 5 and time.perf_counter() - wall0 < 3.0:
-        step()
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop()
-    if dist is not None:
-        dist.barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
+    r = time_device_resident(pb, torch, batch, n, m, dev, local, args.steps, args.warmup, dist)
+    step_ms, clocks, launches_per_step, wall = r["step_ms"], r["clocks"], r["launches"], r["wall"]
     total_ms = float(sum(step_ms))
     max_ms = pb.max_over_ranks(total_ms, dist, dev)
     evals_step_rank = float(n) * m
@@ -331,8 +510,7 @@ def run_gpu(args):
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local)
     me = min(m, E2E_MAX_TIMES)
-    del out, err, flush
-    torch.cuda.empty_cache()
+    jd, fr = pb.synth_time_grid(m)
     h_jd = torch.tensor(jd[:me]).pin_memory()
     h_fr = torch.tensor(fr[:me]).pin_memory()
     h_out = torch.empty((6, n, me), dtype=torch.float64).pin_memory()
@@ -346,8 +524,10 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         batch.propagate(h_jd, h_fr, h_out, h_err)  # synchronises: results are on the host
         _ = int(h_err[0, 0])
-    e2e_s = time.perf_counter() - te
-    e2e_value = float(n) * me * world * e2e_steps / pb.max_over_ranks(e2e_s, dist, dev)
+    e2e_s = pb.max_over_ranks(time.perf_counter() - te, dist, dev)
+    e2e_value = float(n) * me * world * e2e_steps / e2e_s
+    e2e_gbs = float(n) * me * world * e2e_steps * BYTES_PER_EVAL / e2e_s * 1e-9
+    codes_ok = float((h_err == 0).double().mean())
     # ---- the same through perturb_gpu_propagate_states: the caller's StateVector[n * m] ----
     del h_out
     h_states = torch.empty((n, me, 8), dtype=torch.float64).pin_memory()
@@ -359,9 +539,32 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         batch.propagate_states(h_jd, h_fr, h_states, h_err)  # synchronises
         _ = int(h_err[0, 0])
-    rec_s = time.perf_counter() - tr
-    rec_value = float(n) * me * world * e2e_steps / pb.max_over_ranks(rec_s, dist, dev)
-    del h_states
+    rec_s = pb.max_over_ranks(time.perf_counter() - tr, dist, dev)
+    rec_value = float(n) * me * world * e2e_steps / rec_s
+    del h_states, h_err
+    # ---- raw D2H ceiling of the box: every rank copies device -> pinned host at the same time
+    # (one cudaMemcpyAsync per repetition), the aggregate is what N GPUs can land in host memory
+    best, mean = pb.capi.C.c_double(0.0), pb.capi.C.c_double(0.0)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    tc = time.perf_counter()
+    ceiling_bytes, ceiling_reps = 1 << 30, 4
+    st = pb.capi.tools().perturb_gpu_measure_d2h(local, ceiling_bytes, ceiling_reps,
+                                                 pb.capi.C.byref(best), pb.capi.C.byref(mean))
+    ceil_s = pb.max_over_ranks(time.perf_counter() - tc, dist, dev)
+    d2h_mean_min = -pb.max_over_ranks(-mean.value, dist, dev)  # slowest rank's rate
+    d2h_mean_sum = mean.value
+    if dist is not None:
+        t = torch.tensor([mean.value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        d2h_mean_sum = float(t.item())
+    ceiling = {"d2h_ceiling_gbs": d2h_mean_sum if st == 0 else None,
+               "d2h_ceiling_gbs_slowest_gpu": d2h_mean_min if st == 0 else None,
+               "d2h_ceiling_how": "all %d ranks at once: %d x cudaMemcpyAsync of 1 GiB device -> "
+                                  "pinned host each (after one untimed copy), sum of the per-rank "
+                                  "mean rates" % (world, ceiling_reps),
+               "d2h_ceiling_wall_s": ceil_s}
     # ---- the fused consumer (N3): host time grid in, one 40-byte summary per satellite out ----
     hs_jd = torch.tensor(jd).pin_memory()
     hs_fr = torch.tensor(fr).pin_memory()
@@ -375,8 +578,58 @@ def run_gpu(args):
     sum_s = time.perf_counter() - ts
     sum_value = float(n) * m * world * e2e_steps / pb.max_over_ranks(sum_s, dist, dev)
     sum_launches = batch.last_launch_count()
+    batch.close()
+    torch.cuda.empty_cache()
+    # ---- the drop-in call itself: C++ user code, std::vector destinations (one process per GPU)
+    dropin = None
+    try:
+        if dist is not None:
+            dist.barrier()
+        dropin = dropin_harness(args.workload, local, max(2, min(args.steps, 3)))
+        drop_s = pb.max_over_ranks(dropin["dropin_ms"], dist, dev) * 1e-3
+        pin_s = pb.max_over_ranks(dropin["pinned_ms"], dist, dev) * 1e-3
+        dn = float(dropin["satellites"]) * dropin["times"] * world
+        dropin = {
+            "value": dn / drop_s, "unit": "evals/s",
+            "what": "perturb::SatelliteBatch::propagate(times, m, svs, errs) from a C++ program "
+                    "(tests/cpp/dropin_bench.cpp): std::vector<StateVector> + std::vector<Sgp4Error> "
+                    "destinations (pageable), untouched-on-error semantics, wall clock per call",
+            "ms_per_call": drop_s * 1e3,
+            "h2d_bytes_per_step": int(2 * dropin["times"] * 8),
+            "d2h_bytes_per_step": int(float(dropin["satellites"]) * dropin["times"] * 68),
+            "steps": dropin["steps"],
+            "pinned_states_value": dn / pin_s if pin_s > 0 else None,
+            "ratio_to_pinned_states": pin_s / drop_s if drop_s > 0 else None,
+            "equals_pinned_states_bit_for_bit": dropin["dropin_equals_pinned"],
+            "ok_fraction": dropin["ok_fraction"],
+        }
+    except Exception as exc:  # the harness is evidence, not the metric: report, do not die
+        dropin = {"value": None, "error": "%s: %s" % (type(exc).__name__, exc)}
     os.sched_setaffinity(0, all_cpus)  # the CPU arm below uses every host core again
-    codes_ok = float((h_err == 0).double().mean())
+
+    # ---- the other BASELINE configs, device-resident, full size ----
+    prof = load_profile_counts()
+    workloads = {}
+    if not args.no_extra:
+        xsteps = 3
+        if world == 1:
+            for name in ("c3", "c4", "c5"):
+                workloads[name] = extra_workload(pb, torch, name, rank, world, local, dev, dist,
+                                                 fp64_peak, prof, xsteps)
+        else:
+            # strong scaling of config 5 as BASELINE.json states it: 1 M satellites x 10 000
+            # times over N GPUs, time-chunked where 52 B x evaluations exceed the device memory
+            workloads["c5_strong"] = extra_workload(pb, torch, "c5", rank, world, local, dev, dist,
+                                                    fp64_peak, prof, xsteps, total=1000000)
+            workloads["c5_strong"]["scaling"] = "strong"
+    inproc = None
+    if world > 1 and not args.no_extra:
+        if rank == 0:
+            try:
+                inproc = inproc_sharded(pb, torch, args.workload, world, 5)
+            except Exception as exc:
+                inproc = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        dist.barrier()  # the other ranks wait here, their GPUs idle
 
     if rank != 0:
         if dist is not None:
@@ -392,23 +645,23 @@ def run_gpu(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    pipe = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic = prof.get(args.workload)
-        # FP64 instructions per evaluation of each class kernel, counted by ncu (profiles/):
-        # the share of the FP64 pipe's issue cycles (2 warp instructions per clock per SM) the
-        # step keeps busy -- the quantity that bounds this kernel, next to the flops-v0 figure
-        ipe = prof.get("fp64_instr_per_eval")
-        if ipe and clocks.get("sm_mhz"):
-            instr = float(sum(ipe[c] * cls[c] for c in range(5))) * m / 32.0
-            cap = launch_ms * 1e-3 * clocks["sm_mhz"] * 1e6 * N_SM * 2.0
-            pipe = {"fp64_warp_instr_per_step": instr, "frac_of_fp64_issue_cycles": instr / cap,
-                    "fp64_instr_per_eval": ipe, "source": prof.get("_fp64_instr_source")}
-    except Exception:
-        pass
-    cpu = cpu_arm(args.workload, 2, 1) if world == 1 or rank == 0 else None
+    traffic = prof.get(args.workload)
+    pipe = fp64_pipe_share(prof, cls, m, launch_ms, clocks.get("sm_mhz"))
+    cpu = cpu_arm(args.workload, 2, 1)
+    e2e = {
+        "value": e2e_value,
+        "unit": "evals/s",
+        "h2d_bytes_per_step": int(2 * me * 8),
+        "d2h_bytes_per_step": int(float(n) * me * 52),
+        "times_per_step": me,
+        "steps": e2e_steps,
+        "host_buffers": "pinned",
+        "placement": numa,
+        "d2h_gbs": e2e_gbs,
+    }
+    e2e.update(ceiling)
+    if ceiling["d2h_ceiling_gbs"]:
+        e2e["frac_of_ceiling"] = e2e_gbs / ceiling["d2h_ceiling_gbs"]
     line = {
         "metric": "SGP4 evals/sec (sat x time)",
         "value": value,
@@ -422,17 +675,10 @@ def run_gpu(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD_TEXT[args.workload],
-            "satellites_per_gpu": n, "times": m, "evals_per_step": evals_step_rank * world,
-            "orbit_classes": {"near_full": int(cls[0]), "near_simplified": int(cls[1]),
-                              "deep_nonresonant": int(cls[2]), "deep_24h": int(cls[3]),
-                              "deep_12h": int(cls[4])},
-            "sharding": "satellite ranges, one process per GPU, no data-path collective",
-            "l2": "256 MiB buffer rewritten between timed iterations (outside the event pair); "
-                  "each step also writes %.2f GB of outputs" % (evals_step_rank * 52 / 1e9),
-            "outputs": "device-resident SoA planes [6][n][m] f64 + err [n][m] i32",
-        },
+        "config": config_of(args.workload, n, m, world),
+        "orbit_classes": {"near_full": int(cls[0]), "near_simplified": int(cls[1]),
+                          "deep_nonresonant": int(cls[2]), "deep_24h": int(cls[3]),
+                          "deep_12h": int(cls[4])},
         "roofline": {
             "bound": "fp64",
             "achieved": achieved_tflops,
@@ -460,16 +706,7 @@ def run_gpu(args):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
         },
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {
-            "value": e2e_value,
-            "unit": "evals/s",
-            "h2d_bytes_per_step": int(2 * me * 8),
-            "d2h_bytes_per_step": int(float(n) * me * 52),
-            "times_per_step": me,
-            "steps": e2e_steps,
-            "host_buffers": "pinned",
-            "placement": numa,
-        },
+        "e2e": e2e,
         "e2e_states": {
             "value": rec_value,
             "unit": "evals/s",
@@ -479,6 +716,7 @@ def run_gpu(args):
             "d2h_bytes_per_step": int(float(n) * me * 68),
             "steps": e2e_steps,
         },
+        "e2e_dropin": dropin,
         "e2e_summary": {
             "value": sum_value,
             "unit": "evals/s",
@@ -490,6 +728,8 @@ def run_gpu(args):
             "launches_per_step": int(sum_launches),
             "ok_fraction": float(summ["n_ok"].sum()) / (float(n) * m),
         },
+        "workloads": workloads,
+        "inproc_sharded": inproc,
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
         "init": {"satellites": n, "host_parse_ms": 1e3 * t_parse,
@@ -512,6 +752,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--quick", action="store_true",
                     help="device-resident timing only (no e2e, no CPU arm): kernel tuning sweeps")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the other BASELINE configs and the in-process multi-GPU check")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,6 +28,7 @@
 #include <thread>
 #include <vector>
 
+#include "../perturb_elsetrec_layout.h"
 #include "../perturb_gpu.h"
 #include "batch_types.hpp"
 
@@ -202,6 +203,38 @@ public:
         );
     }
 
+    /// Fills `records` -- an array of the reference's `sgp4::elsetrec`, or equally of
+    /// `perturb::Satellite` (its only member is the public `sat_rec`, perturb.hpp:244), record
+    /// i at byte `i * stride` -- with what `sgp4init` left for satellite i (every numeric
+    /// member, error / isimp / irez, method, init, operationmode, t = 0). Identity members
+    /// (satnum, classification, epochyr ...) are left as they are. Host memory.
+    int export_records(void *records, std::size_t stride) {
+        return status_ = perturb_gpu_export_records(handle_, records, stride);
+    }
+
+    /// What ONE `sats[i].propagate(t, sv)` leaves in `sats[i].sat_rec` besides the state: t,
+    /// error, the mean elements am .. nm (sgp4.cpp:1801-1802, 1895-1901), for deep-space
+    /// satellites aycof / xlcof / con41 / x1mth2 / x7thm1 and the resonance integrator state.
+    int write_back_records(const JulianDate &t, void *records, std::size_t stride) {
+        return status_ = perturb_gpu_write_back(handle_, t.jd, t.jd_frac, 1, records, stride);
+    }
+    /// The same for `propagate_from_epoch(mins, sv)`.
+    int write_back_records_from_epoch(double mins, void *records, std::size_t stride) {
+        return status_ = perturb_gpu_write_back(handle_, mins, 0.0, 0, records, stride);
+    }
+
+#ifdef PERTURB_PERTURB_HPP  // perturb's own headers are present: the typed forms
+    /// `sats[i].sat_rec` <- the batch's initialised record, i < size().
+    int export_records(Satellite *sats) { return export_records(sats, sizeof(Satellite)); }
+    /// `sats[i].sat_rec` as `sats[i].propagate(t, sv)` would leave it, i < size().
+    int write_back(Satellite *sats, const JulianDate &t) {
+        return write_back_records(t, sats, sizeof(Satellite));
+    }
+    int write_back_from_epoch(Satellite *sats, double mins) {
+        return write_back_records_from_epoch(mins, sats, sizeof(Satellite));
+    }
+#endif
+
     perturb_gpu_batch *handle() { return handle_; }
 
 private:
@@ -251,6 +284,17 @@ private:
             status_ = perturb_gpu_epoch(handle_, epoch_jd_.data(), epoch_frac_.data());
         }
     }
+
+#ifdef PERTURB_PERTURB_HPP
+    // The generated layout table (include/perturb_elsetrec_layout.h) against the real struct:
+    // a reference whose record moved does not compile instead of being written at wrong offsets.
+    static_assert(sizeof(sgp4::elsetrec) == PERTURB_ELSETREC_SIZE, "elsetrec size moved");
+    static_assert(sizeof(Satellite) == sizeof(sgp4::elsetrec), "Satellite is its sat_rec");
+#  define PERTURB_BATCH_CHECK_MEMBER(name, offset, kind) \
+    static_assert(offsetof(sgp4::elsetrec, name) == offset, "elsetrec member moved: " #name);
+    PERTURB_ELSETREC_MEMBERS(PERTURB_BATCH_CHECK_MEMBER)
+#  undef PERTURB_BATCH_CHECK_MEMBER
+#endif
 
     // `StateVector` / `Sgp4Error` are handed to the C ABI as they are.
     static_assert(sizeof(StateVector) == sizeof(perturb_gpu_state), "StateVector is 64 bytes");

@@ -274,6 +274,33 @@ const char *perturb_gpu_record_field_name(int field);
 /* out [n] host, caller order. */
 int perturb_gpu_record_field(const perturb_gpu_batch *batch, int field, double *out);
 
+/* ---- write-back into the reference's own records ---------------------- */
+
+/* sizeof(perturb::sgp4::elsetrec) == sizeof(perturb::Satellite) the layout table was generated
+ * for (include/perturb_elsetrec_layout.h, from include/perturb/sgp4.hpp:89-134): 1000. */
+int perturb_gpu_elsetrec_size(void);
+
+/* Fills an array of the reference's `sgp4::elsetrec` (equally: of `perturb::Satellite`, whose
+ * only member is the public `sat_rec`, include/perturb/perturb.hpp:244) with the state
+ * `sgp4init` left: every numeric member the batch carries, error / isimp / irez, method, init
+ * and operationmode, t = 0. Members that only identify the object (satnum, classification,
+ * intldesg, epochyr, epochdays, ephtype, elnum, revnum ...) are NOT touched: build the records
+ * with the reference's constructor, or zero them, first. `records` is HOST memory,
+ * record i at byte i * stride, stride >= perturb_gpu_elsetrec_size(); caller order. */
+int perturb_gpu_export_records(const perturb_gpu_batch *batch, void *records, size_t stride);
+
+/* What ONE call `sats[i].propagate(JulianDate(jd, jd_frac), sv)` (use_jd != 0) or
+ * `sats[i].propagate_from_epoch(jd, sv)` (use_jd == 0, `jd` = minutes) leaves in `sat_rec`
+ * besides the state it returns, for every satellite i: t and error (src/sgp4.cpp:1801-1802),
+ * the singly averaged mean elements am, em, im, Om, om, mm, nm where the reference stores them
+ * (:1895-1901; not for codes 1 and 2), for deep-space satellites aycof, xlcof (:1952-1957) and
+ * con41, x1mth2, x7thm1 (:2017-2019), and for resonant ones the integrator state atime, xli,
+ * xni (:1143-1147). The reference's results never depend on that state (restarted and resumed
+ * integrator walks are bit-identical), so this is for callers that READ sat_rec. Same
+ * `records` conventions as perturb_gpu_export_records; synchronous. */
+int perturb_gpu_write_back(perturb_gpu_batch *batch, double jd, double jd_frac, int use_jd,
+                           void *records, size_t stride);
+
 /* Number of kernel launches the last propagate call on this handle issued. */
 int perturb_gpu_last_launch_count(const perturb_gpu_batch *batch);
 

@@ -82,6 +82,46 @@ def _ptr(x):
     return x.data_ptr()  # torch tensor
 
 
+def _dtype_name(x):
+    return str(x.dtype).replace("torch.", "")
+
+
+def _times(x, what):
+    """A time-grid argument as the C ABI reads it: float64, one-dimensional, contiguous. Numpy
+    arrays and Python sequences are converted; tensors must already be right (a silent copy of
+    a device tensor would hide a caller's mistake)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray) or not hasattr(x, "data_ptr"):
+        arr = np.ascontiguousarray(x, dtype=np.float64)
+        if arr.ndim != 1:
+            raise ValueError("%s must be one-dimensional" % what)
+        return arr
+    if _dtype_name(x) != "float64":
+        raise TypeError("%s must be float64, got %s" % (what, _dtype_name(x)))
+    if x.dim() != 1 or (x.numel() > 1 and x.stride(0) != 1):
+        raise ValueError("%s must be a contiguous one-dimensional tensor" % what)
+    return x
+
+
+def _elem_strides(x):
+    if isinstance(x, np.ndarray):
+        return [st // x.itemsize for st in x.strides]
+    return list(x.stride())
+
+
+def _check_output(x, what, dtype, shape_min, last_contiguous=True):
+    """An output buffer as the C ABI writes it: the right element type, at least the given
+    shape, the last axis contiguous."""
+    if _dtype_name(x) != dtype:
+        raise TypeError("%s must be %s, got %s" % (what, dtype, _dtype_name(x)))
+    shape = tuple(x.shape)
+    if len(shape) != len(shape_min) or any(a < b for a, b in zip(shape, shape_min)):
+        raise ValueError("%s has shape %s, need at least %s" % (what, shape, tuple(shape_min)))
+    if last_contiguous and shape[-1] > 1 and _elem_strides(x)[-1] != 1:
+        raise ValueError("%s: the last axis must be contiguous" % what)
+
+
 COE_NAMES = (
     "semilatus_rectum semimajor_axis eccentricity inclination raan arg_of_perigee "
     "true_anomaly mean_anomaly arg_of_latitude true_longitude longitude_of_periapsis").split()
@@ -152,6 +192,8 @@ class SatelliteBatch:
         host. lines1/lines2: lists of strings, or fixed-stride byte blocks with `n` given."""
         if isinstance(lines1, (bytes, bytearray)):
             b1, b2 = bytes(lines1), bytes(lines2)
+            if n is None or min(len(b1), len(b2)) < n * capi.SYNTH_LINE_STRIDE:
+                raise ValueError("line blocks shorter than n * %d bytes" % capi.SYNTH_LINE_STRIDE)
         else:
             n = len(lines1)
             b1, b2 = _as_line_block(lines1), _as_line_block(lines2)
@@ -252,14 +294,27 @@ class SatelliteBatch:
         plane = s[0]
         return row, max(plane, n * row)  # row_stride, plane_stride (doubles)
 
+    def _checked_planes(self, m, posvel, err):
+        """Validated (posvel, err, row_stride, plane_stride) of a planes-mode call."""
+        posvel, err = self._outputs(m, posvel, err)
+        _check_output(posvel, "posvel", "float64", (6, self.n, m))
+        _check_output(err, "err", "int32", (self.n, m))
+        row, plane = self._strides(posvel, self.n, m)
+        if self.n > 1 and m > 0 and _elem_strides(err)[0] != row:
+            raise ValueError("err row stride (%d) differs from posvel row stride (%d)"
+                             % (_elem_strides(err)[0], row))
+        return posvel, err, row, plane
+
     def propagate(self, jd, jd_frac, posvel=None, err=None, stream=None, sync=True):
         """All satellites x all JulianDate(jd[k], jd_frac[k]).
 
         Returns (posvel [6, n, m] = x,y,z [km], vx,vy,vz [km/s]; err [n, m] Sgp4Error).
         jd/jd_frac/posvel/err may be numpy arrays (host) or torch CUDA tensors (device)."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
         m = int(jd.shape[0])
-        posvel, err = self._outputs(m, posvel, err)
-        row, plane = self._strides(posvel, self.n, m)
+        if int(jd_frac.shape[0]) != m:
+            raise ValueError("jd and jd_frac differ in length")
+        posvel, err, row, plane = self._checked_planes(m, posvel, err)
         st = capi.lib().perturb_gpu_propagate(
             self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(posvel), _ptr(err), row, plane, stream)
         capi.check(st, "perturb_gpu_propagate")
@@ -276,11 +331,25 @@ class SatelliteBatch:
         of 64-byte perturb::StateVector records: returns (states [n, m] STATE_DTYPE, err [n, m]).
         `states` / `err` may be given: numpy arrays (host, STATE_DTYPE / int32) or CUDA torch
         tensors (float64 [n, m, 8] / int32 [n, m])."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
         m = int(jd.shape[0])
         if states is None:
             states = np.empty((self.n, m), dtype=self.STATE_DTYPE)
-            err = np.empty((self.n, m), dtype=np.int32)
-        row = int(states.stride(0) // 8) if hasattr(states, "is_cuda") else int(states.strides[0] // 64)
+            if err is None:
+                err = np.empty((self.n, m), dtype=np.int32)
+        if err is None:
+            raise ValueError("give err together with states")
+        _check_output(err, "err", "int32", (self.n, m))
+        if hasattr(states, "is_cuda"):
+            _check_output(states, "states", "float64", (self.n, m, 8))
+            row = int(states.stride(0) // 8)
+        else:
+            if states.dtype != self.STATE_DTYPE:
+                raise TypeError("states must have STATE_DTYPE")
+            _check_output(states, "states", str(states.dtype), (self.n, m))
+            row = int(states.strides[0] // 64)
+        if self.n > 1 and m > 0 and _elem_strides(err)[0] != row:
+            raise ValueError("err row stride differs from the states row stride")
         st = capi.lib().perturb_gpu_propagate_states(
             self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(states), _ptr(err), row, stream)
         capi.check(st, "perturb_gpu_propagate_states")
@@ -315,6 +384,7 @@ class SatelliteBatch:
     def propagate_summary(self, jd, jd_frac=None, stream=None):
         """Fused consumer: per-satellite envelope of a propagation (numpy structured array [n],
         SUMMARY_DTYPE) without materialising the [n, m] states. jd_frac None: jd = minutes."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
         out = np.zeros(self.n, dtype=self.SUMMARY_DTYPE)
         assert out.dtype.itemsize == C.sizeof(capi.Summary)
         st = capi.lib().perturb_gpu_propagate_summary(
@@ -331,10 +401,53 @@ class SatelliteBatch:
             self._h, _ptr(jd), _ptr(jd_frac), int(jd.shape[0]), out.data_ptr(), stream)
         capi.check(st, "perturb_gpu_propagate_summary")
 
+    def propagate_into(self, jd, jd_frac, states, err=None):
+        """The drop-in loop `errs[i, k] = sats[i].propagate(times[k], svs[i, k])` into the
+        caller's own HOST arrays (perturb_gpu_propagate_into): `states` [n, m] STATE_DTYPE is
+        updated in place -- epoch always, position / velocity for codes NONE and DECAYED only,
+        otherwise left as they were, like the reference. jd_frac None: jd = minutes."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
+        m = int(jd.shape[0])
+        if not isinstance(states, np.ndarray) or states.dtype != self.STATE_DTYPE:
+            raise TypeError("states must be a numpy array of STATE_DTYPE")
+        _check_output(states, "states", str(states.dtype), (self.n, m))
+        row = int(states.strides[0] // 64)
+        if err is not None:
+            _check_output(err, "err", "int32", (self.n, m))
+            if self.n > 1 and m > 0 and _elem_strides(err)[0] != row:
+                raise ValueError("err row stride differs from the states row stride")
+        st = capi.lib().perturb_gpu_propagate_into(
+            self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(states), _ptr(err), row)
+        capi.check(st, "perturb_gpu_propagate_into")
+        return states, err
+
+    # ---- write-back into the reference's own records (N2) -------------------------------
+    def export_records(self, records=None, stride=None):
+        """The initialised `sgp4::elsetrec` of every satellite as the reference lays it out
+        (perturb_gpu_export_records): uint8 array [n, stride], stride >= 1000."""
+        size = capi.lib().perturb_gpu_elsetrec_size()
+        if records is None:
+            records = np.zeros((self.n, stride or size), dtype=np.uint8)
+        _check_output(records, "records", "uint8", (self.n, size))
+        st = capi.lib().perturb_gpu_export_records(self._h, records.ctypes.data, records.strides[0])
+        capi.check(st, "perturb_gpu_export_records")
+        return records
+
+    def write_back(self, records, jd, jd_frac=None):
+        """What ONE propagate call at JulianDate(jd, jd_frac) (or minutes `jd` when jd_frac is
+        None) leaves in `sat_rec`, written into `records` [n, stride] uint8 in place."""
+        size = capi.lib().perturb_gpu_elsetrec_size()
+        _check_output(records, "records", "uint8", (self.n, size))
+        st = capi.lib().perturb_gpu_write_back(
+            self._h, float(jd), 0.0 if jd_frac is None else float(jd_frac),
+            0 if jd_frac is None else 1, records.ctypes.data, records.strides[0])
+        capi.check(st, "perturb_gpu_write_back")
+        return records
+
     def propagate_from_epoch(self, mins, posvel=None, err=None, stream=None, sync=True):
+        mins = _times(mins, "mins")
         m = int(mins.shape[0])
-        posvel, err = self._outputs(m, posvel, err)
-        row, plane = self._strides(posvel, self.n, m)
+        posvel, err, row, plane = self._checked_planes(m, posvel, err)
         st = capi.lib().perturb_gpu_propagate_from_epoch(
             self._h, _ptr(mins), m, _ptr(posvel), _ptr(err), row, plane, stream)
         capi.check(st, "perturb_gpu_propagate_from_epoch")

@@ -36,7 +36,8 @@ EXPORTS = (
     "perturb_gpu_device perturb_gpu_last_error perturb_gpu_epoch perturb_gpu_orbit_class "
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles perturb_gpu_parse_tle "
-    "perturb_gpu_propagate_into"
+    "perturb_gpu_propagate_into perturb_gpu_elsetrec_size perturb_gpu_export_records "
+    "perturb_gpu_write_back"
 ).split()
 # ... and include/perturb_benchtools.h + include/perturb_synth.h (libperturb_benchtools.so)
 TOOLS_EXPORTS = (
@@ -108,7 +109,14 @@ def lib():
     L.perturb_gpu_strerror.restype = C.c_char_p
     L.perturb_gpu_parse_tles.argtypes = [
         C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(Tle), ip]
-    L.perturb_gpu_propagate_into.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
+    try:
+        L.perturb_gpu_propagate_into.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
+        L.perturb_gpu_export_records.argtypes = [vp, vp, C.c_size_t]
+        L.perturb_gpu_write_back.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, C.c_size_t]
+    except AttributeError:
+        # an older comparison build loaded through PERTURB_GPU_LIB (kernel sweeps only)
+        if "PERTURB_GPU_LIB" not in os.environ:
+            raise
     _lib = L
     return L
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/perturb_gpu.h"
+#include "../../include/perturb_elsetrec_layout.h"
 #include "batch_internal.h"
 #include "host_workers.h"
 
@@ -24,6 +25,12 @@ int fail(int status, const std::string &msg) {
     g_last_error = msg;
     return status;
 }
+
+}  // namespace
+
+int pb::report_failure(int status, const char *msg) { return fail(status, msg ? msg : ""); }
+
+namespace {
 
 #define PB_CUDA(call)                                                                        \
     do {                                                                                     \
@@ -1075,6 +1082,147 @@ int perturb_gpu_record_field(const perturb_gpu_batch *batch, int field, double *
     DeviceGuard guard(batch->device);
     PB_CUDA(cudaMemcpy(out, batch->d_rec + static_cast<size_t>(field) * batch->n,
                        batch->n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PERTURB_GPU_OK;
+}
+
+namespace {
+
+// Members of sgp4::elsetrec by name (generated table, include/perturb_elsetrec_layout.h).
+struct Member {
+    const char *name;
+    size_t offset;
+    char kind;  // d double, i int, c char
+};
+const Member kMembers[] = {
+#define X(name, offset, kind) {#name, offset, #kind[0]},
+    PERTURB_ELSETREC_MEMBERS(X)
+#undef X
+};
+
+const Member *find_member(const char *name) {
+    for (const Member &m : kMembers) {
+        if (std::strcmp(m.name, name) == 0) return &m;
+    }
+    return nullptr;
+}
+
+inline void put_double(void *records, size_t stride, size_t i, const Member *m, double v) {
+    std::memcpy(static_cast<char *>(records) + i * stride + m->offset, &v, sizeof(double));
+}
+inline void put_int(void *records, size_t stride, size_t i, const Member *m, int v) {
+    std::memcpy(static_cast<char *>(records) + i * stride + m->offset, &v, sizeof(int));
+}
+inline void put_char(void *records, size_t stride, size_t i, const Member *m, char v) {
+    static_cast<char *>(records)[i * stride + m->offset] = v;
+}
+
+}  // namespace
+
+int perturb_gpu_elsetrec_size(void) { return PERTURB_ELSETREC_SIZE; }
+
+int perturb_gpu_export_records(const perturb_gpu_batch *batch, void *records, size_t stride) {
+    if (batch == nullptr || records == nullptr || stride < PERTURB_ELSETREC_SIZE) {
+        return fail(PERTURB_GPU_ERR_ARG, "null argument or stride below sizeof(sgp4::elsetrec)");
+    }
+    const size_t n = batch->n;
+    if (n == 0) return PERTURB_GPU_OK;
+    DeviceGuard guard(batch->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    std::vector<double> plane(n);
+    for (int f = 0; f < RF_COUNT; ++f) {
+        const char *name = kRecordFieldNames[f];
+        const bool is_method = std::strcmp(name, "method_d") == 0;
+        const Member *m = find_member(is_method ? "method" : name);
+        if (m == nullptr) continue;
+        PB_CUDA(cudaMemcpy(plane.data(), batch->d_rec + static_cast<size_t>(f) * n,
+                           n * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) {
+            if (is_method) {
+                put_char(records, stride, i, m, plane[i] != 0.0 ? 'd' : 'n');
+            } else if (m->kind == 'd') {
+                put_double(records, stride, i, m, plane[i]);
+            } else if (m->kind == 'i') {
+                put_int(records, stride, i, m, static_cast<int>(plane[i]));
+            }
+        }
+    }
+    // what sgp4init leaves besides the numbers: init = 'n' (src/sgp4.cpp:1678), the operation
+    // mode it was called with, and t = 0 from its closing sgp4(t = 0) call (:1801)
+    const Member *m_init = find_member("init"), *m_ops = find_member("operationmode"),
+                 *m_t = find_member("t");
+    for (size_t i = 0; i < n; ++i) {
+        if (batch->init_error[i] == PERTURB_SGP4_INVALID_TLE) continue;  // never initialised
+        put_char(records, stride, i, m_init, 'n');
+        put_char(records, stride, i, m_ops, batch->opsmode_a ? 'a' : 'i');
+        put_double(records, stride, i, m_t, 0.0);
+    }
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_write_back(perturb_gpu_batch *b, double jd, double jd_frac, int use_jd,
+                           void *records, size_t stride) {
+    if (b == nullptr || records == nullptr || stride < PERTURB_ELSETREC_SIZE) {
+        return fail(PERTURB_GPU_ERR_ARG, "null argument or stride below sizeof(sgp4::elsetrec)");
+    }
+    const size_t n = b->n;
+    if (n == 0) return PERTURB_GPU_OK;
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    ScratchFree scratch;  // [0] planes, [1] classes
+    PB_CUDA(cudaMalloc(&scratch.p[0], static_cast<size_t>(pb::WB_COUNT) * n * sizeof(double)));
+    PB_CUDA(cudaMalloc(&scratch.p[1], n));
+    PB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_call, 0));
+    PB_CUDA(cudaMemcpyAsync(scratch.p[1], b->cls.data(), n, cudaMemcpyHostToDevice, b->stream));
+    pb::PropLaunch l;
+    fill_launch(b, l);
+    l.use_jd = use_jd ? 1 : 0;
+    l.n = n;
+    pb::launch_write_back(l, static_cast<const uint8_t *>(scratch.p[1]), jd, jd_frac,
+                          static_cast<double *>(scratch.p[0]), b->stream);
+    PB_CUDA(cudaGetLastError());
+    std::vector<double> wb(static_cast<size_t>(pb::WB_COUNT) * n);
+    PB_CUDA(cudaMemcpyAsync(wb.data(), scratch.p[0], wb.size() * sizeof(double),
+                            cudaMemcpyDeviceToHost, b->stream));
+    PB_CUDA(cudaStreamSynchronize(b->stream));
+    b->last_launches = 1;
+
+    const Member *m_t = find_member("t"), *m_err = find_member("error");
+    const Member *m_mean[7] = {find_member("am"), find_member("em"), find_member("im"),
+                               find_member("Om"), find_member("om"), find_member("mm"),
+                               find_member("nm")};
+    const Member *m_deep[5] = {find_member("aycof"), find_member("xlcof"), find_member("con41"),
+                               find_member("x1mth2"), find_member("x7thm1")};
+    const Member *m_res[3] = {find_member("atime"), find_member("xli"), find_member("xni")};
+    auto at = [&](int plane, size_t i) { return wb[static_cast<size_t>(plane) * n + i]; };
+    for (size_t i = 0; i < n; ++i) {
+        if (b->init_error[i] == PERTURB_SGP4_INVALID_TLE) {
+            // a zeroed record: sgp4() sets t, fails the mean-motion check and stores nothing else
+            put_double(records, stride, i, m_t, at(pb::WB_T, i));
+            put_int(records, stride, i, m_err, PERTURB_SGP4_MEAN_MOTION);
+            continue;
+        }
+        put_double(records, stride, i, m_t, at(pb::WB_T, i));
+        put_int(records, stride, i, m_err, static_cast<int>(at(pb::WB_ERROR, i)));
+        const int stage = static_cast<int>(at(pb::WB_STAGE, i));
+        const bool deep = b->cls[i] >= PB_CLS_DEEP_NR;
+        if (stage >= 1) {
+            for (int e = 0; e < 7; ++e) put_double(records, stride, i, m_mean[e], at(pb::WB_AM + e, i));
+        }
+        if (deep && stage >= 2) {
+            put_double(records, stride, i, m_deep[0], at(pb::WB_AYCOF, i));
+            put_double(records, stride, i, m_deep[1], at(pb::WB_XLCOF, i));
+        }
+        if (deep && stage >= 3) {
+            put_double(records, stride, i, m_deep[2], at(pb::WB_CON41, i));
+            put_double(records, stride, i, m_deep[3], at(pb::WB_X1MTH2, i));
+            put_double(records, stride, i, m_deep[4], at(pb::WB_X7THM1, i));
+        }
+        if (at(pb::WB_RESONANT, i) != 0.0) {
+            put_double(records, stride, i, m_res[0], at(pb::WB_ATIME, i));
+            put_double(records, stride, i, m_res[1], at(pb::WB_XLI, i));
+            put_double(records, stride, i, m_res[2], at(pb::WB_XNI, i));
+        }
+    }
     return PERTURB_GPU_OK;
 }
 

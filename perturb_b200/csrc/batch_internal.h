@@ -13,6 +13,9 @@ namespace pb {
 struct GravModelConsts;
 struct TleNumbers;
 
+// Records `msg` as the calling thread's perturb_gpu_strerror() text and returns `status`.
+int report_failure(int status, const char *msg);
+
 struct GravAll {  // host copy of getgravconst(), src/sgp4.cpp:2101-2157
     double tumin, mus, radiusearthkm, xke, j2, j3, j4, j3oj2;
 };
@@ -76,6 +79,19 @@ struct PropLaunch {
 // Kernel 2, one launch per non-empty class. Returns the number of launches issued, or -1 when
 // the grid (satellite tiles x time tiles) exceeds what one launch can cover.
 int launch_sgp4_propagate(const PropLaunch &p, cudaStream_t stream);
+
+// Planes of the write-back pass, wb[WB_COUNT][n] in caller order (error, stage and resonant
+// are small integers stored as doubles).
+enum {
+    WB_T = 0, WB_ERROR, WB_STAGE, WB_AM, WB_EM, WB_IM, WB_OMEGA, WB_ARGP, WB_MM, WB_NM,
+    WB_AYCOF, WB_XLCOF, WB_CON41, WB_X1MTH2, WB_X7THM1, WB_RESONANT, WB_ATIME, WB_XLI, WB_XNI,
+    WB_COUNT
+};
+
+// One evaluation per satellite at the time (ta, tb) [JulianDate pair, or minutes with use_jd
+// = 0 in `l`], side outputs only; d_cls [n] orbit class per satellite, caller order.
+void launch_write_back(const PropLaunch &l, const uint8_t *d_cls, double ta, double tb,
+                       double *d_wb, cudaStream_t stream);
 
 // Number of per-satellite partial records the summary mode needs for a grid of m times.
 size_t summary_chunks(size_t m);

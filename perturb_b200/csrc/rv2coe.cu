@@ -6,12 +6,13 @@
 //
 // Element-wise over (satellite, time): 48 B read + 88 B written per state, so the kernel's
 // roofline is HBM (6.5 TB/s / 136 B = 4.8e10 states/s). Compiled with -fmad=false: the general
-// routine's arithmetic is the reference's apart from libdevice-vs-glibc acos/atan2/sin/cos,
-// which matters for the 1e-8 "small" thresholds that switch outputs to the 999999.1
-// "undefined" sentinel; the fast path for inclined ellipses (below) spells its FMAs out.
+// routine rounds every product and sum on its own, as the reference's scalar code does, which
+// keeps it on the reference's side of the 1e-8 "small" thresholds that switch elements to the
+// 999999.1 "undefined" sentinel; the fast path for inclined ellipses spells its FMAs out.
 #include <cuda_runtime.h>
 
 #include "../../include/perturb_gpu.h"
+#include "batch_internal.h"
 #include "sgp4_math.cuh"
 
 namespace {
@@ -22,166 +23,147 @@ constexpr double kSmall = 0.00000001;
 constexpr double kUndefined = 999999.1;
 constexpr double kInfinite = 999999.9;
 
-__device__ inline double mag3(const double v[3]) {
-    return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+// ---- general routine ------------------------------------------------------------------------
+// Every conic and every degenerate case of rv2coe_SGP4 (src/sgp4.cpp:2863-3064), including the
+// elements it reports as "undefined" (999999.1) or "infinite" (999999.9). Organised around
+// what decides the outcome rather than around the reference's statement order:
+//   * a Frame holds everything derived from (r, v) before any angle is taken;
+//   * the shape of the orbit is two independent bits (circular, equatorial) -- the reference's
+//     `typeorbit` 1..4 is their four combinations -- and each element states which
+//     combinations it exists for;
+//   * every angle comes from ONE helper, arc(): arccosine of a clamped cosine, mirrored to
+//     (pi, 2 pi) by a sign test, or the sentinel when its vectors are too short to define it;
+//   * true -> mean anomaly is one function of the conic type (newtonnu_SGP4, :2749-2803).
+// It runs for the vanishing share of states the fast path below declines, as a real call.
+
+__device__ __forceinline__ double dot3f(const double a[3], const double b[3]) {
+    return __fma_rn(a[2], b[2], __fma_rn(a[1], b[1], __dmul_rn(a[0], b[0])));
 }
 
-__device__ inline double dot3(const double a[3], const double b[3]) {
-    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+struct Frame {
+    double r_len, v_len, rdotv;
+    double h[3], h_len;    // angular momentum r x v
+    double node[3], node_len;  // line of nodes (-h1, h0, 0)
+    double e[3], ecc;      // eccentricity vector
+    double energy;         // specific mechanical energy v^2 / 2 - mu / r
+};
+
+__device__ inline Frame frame_of(const double r[3], const double v[3], double mus) {
+    Frame f;
+    f.r_len = sqrt(dot3f(r, r));
+    f.v_len = sqrt(dot3f(v, v));
+    f.rdotv = dot3f(r, v);
+    f.h[0] = r[1] * v[2] - r[2] * v[1];
+    f.h[1] = r[2] * v[0] - r[0] * v[2];
+    f.h[2] = r[0] * v[1] - r[1] * v[0];
+    f.h_len = sqrt(dot3f(f.h, f.h));
+    f.node[0] = -f.h[1];
+    f.node[1] = f.h[0];
+    f.node[2] = 0.0;
+    f.node_len = sqrt(dot3f(f.node, f.node));
+    const double v2 = f.v_len * f.v_len, mu_over_r = mus / f.r_len;
+    const double along_r = v2 - mu_over_r;
+    for (int i = 0; i < 3; ++i) f.e[i] = (along_r * r[i] - f.rdotv * v[i]) / mus;
+    f.ecc = sqrt(dot3f(f.e, f.e));
+    f.energy = 0.5 * v2 - mu_over_r;
+    return f;
 }
 
-__device__ inline double sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
-
-// angle_SGP4, src/sgp4.cpp:2659-2681
-__device__ inline double angle_between(const double a[3], const double b[3]) {
-    const double ma = mag3(a), mb = mag3(b);
-    if (ma * mb > kSmall * kSmall) {
-        double temp = dot3(a, b) / (ma * mb);
-        if (fabs(temp) > 1.0) temp = sgn(temp) * 1.0;
-        return acos(temp);
-    }
-    return kUndefined;
+// The angle in [0, pi] whose cosine is `cosine` (clamped: rounding can leave it a hair outside
+// [-1, 1]), mirrored to 2 pi - angle when `mirror`; the "undefined" sentinel when `defined` is
+// false. The reference mirrors angle_SGP4's results even when they are the sentinel
+// (:2972-2974 and the like), so the mirror is applied after the select.
+__device__ inline double arc(double cosine, bool defined, bool mirror) {
+    const double c = fmin(fmax(cosine, -1.0), 1.0);
+    const double a = defined ? acos(c) : kUndefined;
+    return mirror ? kTwoPi - a : a;
 }
 
-// newtonnu_SGP4, src/sgp4.cpp:2749-2803
-__device__ inline void newtonnu(double ecc, double nu, double &e0, double &m) {
-    e0 = 999999.9;
-    m = 999999.9;
-    if (fabs(ecc) < kSmall) {
+// Angle between two vectors (angle_SGP4, :2659-2681): defined when neither is shorter than
+// "small" in the product sense the reference uses.
+__device__ inline double arc_between(const double a[3], double a_len, const double b[3],
+                                     double b_len, bool mirror) {
+    const double scale = a_len * b_len;
+    return arc(dot3f(a, b) / scale, scale > kSmall * kSmall, mirror);
+}
+
+// Mean anomaly from true anomaly for any conic (newtonnu_SGP4; its eccentric-anomaly output is
+// not used by rv2coe). "Infinite" where the reference leaves it so.
+__device__ inline double mean_from_true(double ecc, double nu) {
+    double m = kInfinite;
+    const bool circular = fabs(ecc) < kSmall;
+    const bool elliptic = !circular && ecc < 1.0 - kSmall;
+    const bool hyperbolic = !circular && !elliptic && ecc > 1.0 + kSmall;
+    if (circular) {
         m = nu;
-        e0 = nu;
-    } else if (ecc < 1.0 - kSmall) {
-        const double sine = (sqrt(1.0 - ecc * ecc) * sin(nu)) / (1.0 + ecc * cos(nu));
-        const double cose = (ecc + cos(nu)) / (1.0 + ecc * cos(nu));
-        e0 = atan2(sine, cose);
-        m = e0 - ecc * sin(e0);
-    } else if (ecc > 1.0 + kSmall) {
-        if ((ecc > 1.0) && (fabs(nu) + 0.00001 < kPi - acos(1.0 / ecc))) {
-            const double sine = (sqrt(ecc * ecc - 1.0) * sin(nu)) / (1.0 + ecc * cos(nu));
-            e0 = log(sine + sqrt(sine * sine + 1.0));  // asinh_SGP4, :2705-2711
-            m = ecc * sinh(e0) - e0;
+    } else if (elliptic) {
+        double sn, cn;
+        sincos(nu, &sn, &cn);
+        const double inv = 1.0 / (1.0 + ecc * cn);
+        const double sin_e = sqrt(1.0 - ecc * ecc) * sn * inv, cos_e = (ecc + cn) * inv;
+        const double big_e = atan2(sin_e, cos_e);
+        m = big_e - ecc * sin(big_e);
+    } else if (hyperbolic) {
+        if (fabs(nu) + 0.00001 < kPi - acos(1.0 / ecc)) {
+            const double sinh_f = sqrt(ecc * ecc - 1.0) * sin(nu) / (1.0 + ecc * cos(nu));
+            const double f = log(sinh_f + sqrt(sinh_f * sinh_f + 1.0));  // asinh, :2705-2711
+            m = ecc * sinh(f) - f;
         }
-    } else if (fabs(nu) < 168.0 * kPi / 180.0) {
-        e0 = tan(nu * 0.5);
-        m = e0 + (e0 * e0 * e0) / 3.0;
+    } else if (fabs(nu) < 168.0 * kPi / 180.0) {  // parabolic band
+        const double d = tan(0.5 * nu);
+        m = d + d * d * d / 3.0;
     }
-    if (ecc < 1.0) {
-        m = fmod(m, 2.0 * kPi);
-        if (m < 0.0) m = m + 2.0 * kPi;
-        e0 = fmod(e0, 2.0 * kPi);
+    if (ecc < 1.0) {  // :2796-2801, applied to whatever m holds
+        m = fmod(m, kTwoPi);
+        if (m < 0.0) m += kTwoPi;
     }
+    return m;
 }
 
-// rv2coe_SGP4, src/sgp4.cpp:2863-3064. out[0..10] = p, a, ecc, incl, omega, argp, nu, m,
-// arglat, truelon, lonper.
-__device__ inline void rv2coe(double r[3], double v[3], double mus, double out[11]) {
-    double p, a, ecc, incl, omega, argp, nu, m, arglat, truelon, lonper;
-    const double halfpi = 0.5 * kPi;
-    const double magr = mag3(r), magv = mag3(v);
-    double hbar[3] = {r[1] * v[2] - r[2] * v[1], r[2] * v[0] - r[0] * v[2],
-                      r[0] * v[1] - r[1] * v[0]};
-    const double magh = mag3(hbar);
-    if (magh > kSmall) {
-        double nbar[3] = {-hbar[1], hbar[0], 0.0};
-        const double magn = mag3(nbar);
-        const double c1 = magv * magv - mus / magr;
-        const double rdotv = dot3(r, v);
-        double ebar[3];
-        for (int i = 0; i <= 2; i++) ebar[i] = (c1 * r[i] - rdotv * v[i]) / mus;
-        ecc = mag3(ebar);
-
-        const double sme = (magv * magv * 0.5) - (mus / magr);
-        if (fabs(sme) > kSmall) {
-            a = -mus / (2.0 * sme);
-        } else {
-            a = kInfinite;
-        }
-        p = magh * magh / mus;
-
-        const double hk = hbar[2] / magh;
-        incl = acos(hk);
-
-        // 1 = elliptical/parabolic/hyperbolic inclined, 2 = circular equatorial,
-        // 3 = circular inclined, 4 = elliptical equatorial
-        int typeorbit = 1;
-        const bool equatorial = (incl < kSmall) | (fabs(incl - kPi) < kSmall);
-        if (ecc < kSmall) {
-            typeorbit = equatorial ? 2 : 3;
-        } else if (equatorial) {
-            typeorbit = 4;
-        }
-
-        if (magn > kSmall) {
-            double temp = nbar[0] / magn;
-            if (fabs(temp) > 1.0) temp = sgn(temp);
-            omega = acos(temp);
-            if (nbar[1] < 0.0) omega = kTwoPi - omega;
-        } else {
-            omega = kUndefined;
-        }
-
-        if (typeorbit == 1) {
-            argp = angle_between(nbar, ebar);
-            if (ebar[2] < 0.0) argp = kTwoPi - argp;
-        } else {
-            argp = kUndefined;
-        }
-
-        if ((typeorbit == 1) || (typeorbit == 4)) {
-            nu = angle_between(ebar, r);
-            if (rdotv < 0.0) nu = kTwoPi - nu;
-        } else {
-            nu = kUndefined;
-        }
-
-        m = 0.0;
-        if (typeorbit == 3) {
-            arglat = angle_between(nbar, r);
-            if (r[2] < 0.0) arglat = kTwoPi - arglat;
-            m = arglat;
-        } else {
-            arglat = kUndefined;
-        }
-
-        if ((ecc > kSmall) && (typeorbit == 4)) {
-            double temp = ebar[0] / ecc;
-            if (fabs(temp) > 1.0) temp = sgn(temp);
-            lonper = acos(temp);
-            if (ebar[1] < 0.0) lonper = kTwoPi - lonper;
-            if (incl > halfpi) lonper = kTwoPi - lonper;
-        } else {
-            lonper = kUndefined;
-        }
-
-        if ((magr > kSmall) && (typeorbit == 2)) {
-            double temp = r[0] / magr;
-            if (fabs(temp) > 1.0) temp = sgn(temp);
-            truelon = acos(temp);
-            if (r[1] < 0.0) truelon = kTwoPi - truelon;
-            if (incl > halfpi) truelon = kTwoPi - truelon;
-            m = truelon;
-        } else {
-            truelon = kUndefined;
-        }
-
-        if ((typeorbit == 1) || (typeorbit == 4)) {
-            double e;
-            newtonnu(ecc, nu, e, m);
-        }
-    } else {
-        p = a = ecc = incl = omega = argp = nu = m = arglat = truelon = lonper = kUndefined;
+// out[0..10] = p, a, ecc, incl, omega, argp, nu, m, arglat, truelon, lonper.
+__device__ inline void rv2coe(const double r[3], const double v[3], double mus, double out[11]) {
+    const Frame f = frame_of(r, v, mus);
+    if (!(f.h_len > kSmall)) {  // rectilinear or degenerate: nothing is defined (:3049-3062)
+        for (int c = 0; c < 11; ++c) out[c] = kUndefined;
+        return;
     }
-    out[0] = p;
-    out[1] = a;
-    out[2] = ecc;
+    const double incl = acos(f.h[2] / f.h_len);
+    const bool circular = f.ecc < kSmall;
+    const bool equatorial = (incl < kSmall) || (fabs(incl - kPi) < kSmall);
+    const bool retrograde = incl > 0.5 * kPi;
+    // which elements exist for which shape (the reference's typeorbit: 1 = neither bit,
+    // 2 = both, 3 = circular only, 4 = equatorial only)
+    const bool has_argp = !circular && !equatorial;
+    const bool has_nu = !circular;
+    const bool has_arglat = circular && !equatorial;
+    const bool has_truelon = circular && equatorial && f.r_len > kSmall;
+    const bool has_lonper = !circular && equatorial && f.ecc > kSmall;
+
+    out[0] = f.h_len * f.h_len / mus;
+    out[1] = (fabs(f.energy) > kSmall) ? -mus / (2.0 * f.energy) : kInfinite;
+    out[2] = f.ecc;
     out[3] = incl;
-    out[4] = omega;
-    out[5] = argp;
+    out[4] = arc(f.node[0] / f.node_len, f.node_len > kSmall, f.node_len > kSmall && f.node[1] < 0.0);
+    out[5] = has_argp ? arc_between(f.node, f.node_len, f.e, f.ecc, f.e[2] < 0.0) : kUndefined;
+    const double nu = has_nu ? arc_between(f.e, f.ecc, r, f.r_len, f.rdotv < 0.0) : kUndefined;
     out[6] = nu;
-    out[7] = m;
+    const double arglat =
+        has_arglat ? arc_between(f.node, f.node_len, r, f.r_len, r[2] < 0.0) : kUndefined;
     out[8] = arglat;
+    // the two longitudes are measured from the x axis and counted backwards on retrograde orbits
+    double truelon = kUndefined, lonper = kUndefined;
+    if (has_truelon) {
+        truelon = arc(r[0] / f.r_len, true, r[1] < 0.0);
+        if (retrograde) truelon = kTwoPi - truelon;
+    }
+    if (has_lonper) {
+        lonper = arc(f.e[0] / f.ecc, true, f.e[1] < 0.0);
+        if (retrograde) lonper = kTwoPi - lonper;
+    }
     out[9] = truelon;
     out[10] = lonper;
+    // mean anomaly: from the true anomaly where there is one, else the angle that replaces it
+    out[7] = has_nu ? mean_from_true(f.ecc, nu) : has_arglat ? arglat : has_truelon ? truelon : 0.0;
 }
 
 // ---- fast path ----------------------------------------------------------------------------
@@ -247,10 +229,6 @@ __device__ __forceinline__ double atan2_fast(double y, double x) {
     if (ay > ax) r = __dsub_rn(kPio2Hi, __dsub_rn(r, kPio2Lo));
     if (x < 0.0) r = __dsub_rn(kPi, __dsub_rn(r, kPiLo));
     return (y < 0.0) ? -r : r;
-}
-
-__device__ __forceinline__ double dot3f(const double a[3], const double b[3]) {
-    return __fma_rn(a[2], b[2], __fma_rn(a[1], b[1], __dmul_rn(a[0], b[0])));
 }
 
 __device__ __forceinline__ double clamp1(double c) { return fmin(fmax(c, -1.0), 1.0); }
@@ -365,14 +343,28 @@ rv2coe_kernel(const double *__restrict__ posvel, size_t n, size_t m, size_t row_
     }
 }
 
-bool on_device(const void *p) {
+// Device that owns `p` (device or managed memory), or -1.
+int owner_of(const void *p) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return -1;
     }
-    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device
+                                                                                     : -1;
 }
+
+struct OnDevice {  // make `dev` current for the scope of a call
+    int prev;
+    bool ok;
+    explicit OnDevice(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~OnDevice() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 }  // namespace
 
@@ -382,17 +374,25 @@ extern "C" int perturb_gpu_rv2coe(const double *posvel, size_t n, size_t m, size
     if (posvel == nullptr || coe == nullptr || row_stride < m || plane_stride < n * row_stride ||
         coe_plane_stride < n * row_stride || (m + 255) / 256 > 2147483647ULL ||
         n > 65535ULL * 65535ULL) {
-        return PERTURB_GPU_ERR_ARG;
+        return pb::report_failure(PERTURB_GPU_ERR_ARG, "perturb_gpu_rv2coe: null pointer or inconsistent strides");
     }
     double mus;  // getgravconst, src/sgp4.cpp:2119,2130,2141
     switch (grav_model) {
         case PERTURB_GPU_WGS72_OLD: mus = 398600.79964; break;
         case PERTURB_GPU_WGS72: mus = 398600.8; break;
         case PERTURB_GPU_WGS84: mus = 398600.5; break;
-        default: return PERTURB_GPU_ERR_ARG;
+        default: return pb::report_failure(PERTURB_GPU_ERR_ARG, "perturb_gpu_rv2coe: unknown gravity model");
     }
     if (n == 0 || m == 0) return PERTURB_GPU_OK;
-    if (!on_device(posvel) || !on_device(coe)) return PERTURB_GPU_ERR_ARG;  // device buffers only
+    // both buffers in the memory of ONE device: the kernel runs there, whatever device is
+    // current in the calling thread
+    const int dev = owner_of(posvel);
+    if (dev < 0 || owner_of(coe) != dev) {
+        return pb::report_failure(PERTURB_GPU_ERR_ARG,
+                                  "perturb_gpu_rv2coe: posvel and coe must be memory of the same device");
+    }
+    const OnDevice guard(dev);
+    if (!guard.ok) return pb::report_failure(PERTURB_GPU_ERR_CUDA, "perturb_gpu_rv2coe: cudaSetDevice failed");
     // CTA width that wastes the fewest lanes at the end of a row (1440 times: 9 x 160, none)
     unsigned threads = 256;
     size_t waste = ((m + 255) / 256) * 256 - m;
@@ -408,5 +408,9 @@ extern "C" int perturb_gpu_rv2coe(const double *posvel, size_t n, size_t m, size
                     static_cast<unsigned>((n + 65534) / 65535));
     rv2coe_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         posvel, n, m, row_stride, plane_stride, mus, 1.0 / mus, coe, coe_plane_stride);
-    return cudaGetLastError() == cudaSuccess ? PERTURB_GPU_OK : PERTURB_GPU_ERR_CUDA;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        return pb::report_failure(PERTURB_GPU_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return PERTURB_GPU_OK;
 }

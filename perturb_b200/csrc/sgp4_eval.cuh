@@ -27,6 +27,10 @@
 #include "sgp4_fields.h"
 #include "sgp4_math.cuh"
 
+#ifndef PB_KEPLER_SMALL
+#define PB_KEPLER_SMALL 1  // 0: every orbit through the Newton iteration (bisecting / comparison builds)
+#endif
+
 namespace pb {
 
 // getgravconst() results the evaluation needs (src/sgp4.cpp:2101-2157), batch-wide.
@@ -43,6 +47,10 @@ struct Sgp4Side {  // what sgp4() leaves in the record (src/sgp4.cpp:1895-1901, 
     double am, em, im, Om, om, mm, nm;
     double aycof, xlcof, con41, x1mth2, x7thm1;
     int stage;  // 0: nothing stored, 1: mean elements, 2: + aycof/xlcof, 3: + con41..x7thm1
+    // resonant deep-space satellites: the integrator state dspace() leaves behind
+    // (src/sgp4.cpp:1143-1147), always stored (dspace runs before the first error check)
+    double atime, xli, xni;
+    bool resonant;
 };
 
 template <int CLS>
@@ -297,7 +305,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const bool deep = T::kStatic ? T::kDeep : rt.deep;
     const bool simp = T::kStatic ? T::kSimp : rt.isimp;
     const int irez = T::kStatic ? T::kIrez : rt.irez;
-    if (WANT_SIDE) side->stage = 0;
+    if (WANT_SIDE) {
+        side->stage = 0;
+        side->resonant = false;
+    }
 
     // ---- secular gravity and atmospheric drag, src/sgp4.cpp:1805-1835 ----
     const double xmdf = k(PF_MO) + k(PF_MDOT) * t;
@@ -408,6 +419,12 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
                     resonance_advance(xndt, xldot, xnddt, delt, xli, xni, atime);
                 }
                 resonance_rates(k, irez, xli, xni, atime, xndt, xldot, xnddt);
+            }
+            if (WANT_SIDE) {
+                side->atime = atime;
+                side->xli = xli;
+                side->xni = xni;
+                side->resonant = true;
             }
             const double ft = t - atime;
             nm = xni + xndt * ft + xnddt * ft * ft * 0.5;
@@ -600,7 +617,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     // per lane from the lane's own el2 -- a result never depends on the other lanes of the warp
     // -- while the branches are taken on warp votes, so control flow stays warp-uniform.
     double sineo1, coseo1;
-    if (UNIFORM) {
+    if (UNIFORM && PB_KEPLER_SMALL) {
         const bool small = el2 < kMc[MC_KEPLER_SMALL];
         if (__all_sync(0xffffffffu, small)) {
             kepler_small(u, axnl, aynl, sineo1, coseo1);
@@ -614,7 +631,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             }
         }
     } else {
-        kepler_newton<false>(u, axnl, aynl, sineo1, coseo1);
+        kepler_newton<UNIFORM>(u, axnl, aynl, sineo1, coseo1);
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----

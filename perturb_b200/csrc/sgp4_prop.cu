@@ -660,6 +660,50 @@ summary_reduce_kernel(const perturb_gpu_summary *__restrict__ partials, int chun
     out[i] = r;
 }
 
+// Write-back pass: what ONE `sat.propagate(t, sv)` call leaves in
+// `Satellite::sat_rec` besides the state -- t, error, the singly averaged mean elements
+// (src/sgp4.cpp:1801-1802, 1895-1901), for deep-space satellites aycof / xlcof / con41 / x1mth2 /
+// x7thm1 (:1952-1957, 2017-2019) and for resonant ones the integrator state atime / xli / xni
+// (:1143-1147). One thread per class-sorted slot, class flags at run time; planes in caller
+// order: wb[WB_COUNT][n].
+__global__ void __launch_bounds__(128)
+write_back_kernel(const double *__restrict__ pf, size_t n_pad, const int32_t *__restrict__ perm,
+                  const uint8_t *__restrict__ cls, size_t n, double ta, double tb, int use_jd,
+                  GravConsts g, int opsmode_a, double *__restrict__ wb) {
+    const size_t slot = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (slot >= n_pad) return;
+    const int dst = perm[slot];
+    if (dst < 0) return;
+    const GlobalConsts k = {pf + slot, n_pad};
+    const int c = cls[dst];
+    const ClassFlags rt = {c >= PB_CLS_DEEP_NR, c != PB_CLS_NEAR_FULL,
+                           c == PB_CLS_DEEP_R1 ? 1 : c == PB_CLS_DEEP_R2 ? 2 : 0};
+    const double t = tsince_of(use_jd, ta, tb, k(PF_JD0), k(PF_JDF0));
+    double r[6];
+    Sgp4Side side;
+    const int code = sgp4_eval<PB_CLS_RUNTIME, true, false>(k, g, opsmode_a != 0, rt, t, r, &side);
+    double *o = wb + dst;
+    o[WB_T * n] = t;
+    o[WB_ERROR * n] = static_cast<double>(code);
+    o[WB_STAGE * n] = static_cast<double>(side.stage);
+    o[WB_AM * n] = side.am;
+    o[WB_EM * n] = side.em;
+    o[WB_IM * n] = side.im;
+    o[WB_OMEGA * n] = side.Om;
+    o[WB_ARGP * n] = side.om;
+    o[WB_MM * n] = side.mm;
+    o[WB_NM * n] = side.nm;
+    o[WB_AYCOF * n] = side.aycof;
+    o[WB_XLCOF * n] = side.xlcof;
+    o[WB_CON41 * n] = side.con41;
+    o[WB_X1MTH2 * n] = side.x1mth2;
+    o[WB_X7THM1 * n] = side.x7thm1;
+    o[WB_RESONANT * n] = side.resonant ? 1.0 : 0.0;
+    o[WB_ATIME * n] = side.atime;
+    o[WB_XLI * n] = side.xli;
+    o[WB_XNI * n] = side.xni;
+}
+
 template <int CLS>
 void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &launches) {
     const int tiles = l.tile_count[CLS];
@@ -747,6 +791,20 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
 }
 
 }  // namespace
+
+void launch_write_back(const PropLaunch &l, const uint8_t *d_cls, double ta, double tb,
+                       double *d_wb, cudaStream_t stream) {
+    if (l.n == 0 || l.n_pad == 0) return;
+    GravConsts g;
+    g.radiusearthkm = l.radiusearthkm;
+    g.xke = l.xke;
+    g.j2 = l.j2;
+    g.j3oj2 = l.j3oj2;
+    g.vkmpersec = l.radiusearthkm * l.xke / 60.0;
+    g.inv_xke = 1.0 / l.xke;
+    write_back_kernel<<<static_cast<unsigned>((l.n_pad + 127) / 128), 128, 0, stream>>>(
+        l.pf, l.n_pad, l.perm, d_cls, l.n, ta, tb, l.use_jd, g, l.opsmode_a, d_wb);
+}
 
 size_t summary_chunks(size_t m) {
     return ((m + kTimeTile - 1) / kTimeTile) * kWarps;

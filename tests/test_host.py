@@ -205,3 +205,26 @@ def test_abi_headers_are_plain_c99(tmp_path):
                    'int main(void) { return 0; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only",
                            "-I" + os.path.join(ROOT, "include"), str(src)])
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """bench.py --impl reference times the reference on the CPU: its process may map the
+    benchtools library (catalogue text) and oracle/, never libperturb_gpu.so."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "r = bench.cpu_arm('c2', 1, 0, cores=2, budget_s=0.2)\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libperturb_benchtools.so' in maps\n"
+        "assert 'libperturb_gpu.so' not in maps, 'product library mapped by the reference arm'\n"
+        "print(r['kind'], r['value'] > 0)\n" % ROOT)
+    out = subprocess.run(["python", "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    assert out.stdout.split()[-1] == "True"
+
+
+def test_both_bench_arms_describe_the_same_config():
+    import bench
+    cfg, n, m = bench.WORKLOADS["c2"]
+    assert set(bench.config_of("c2", n, m, 1)) == set(bench.config_of("c2", n, m, 8))
+    assert bench.config_of("c2", n, m, 1)["workload"] == bench.WORKLOAD_TEXT["c2"]
