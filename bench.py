@@ -578,6 +578,53 @@ def run_gpu(args):
     sum_s = time.perf_counter() - ts
     sum_value = float(n) * m * world * e2e_steps / pb.max_over_ranks(sum_s, dist, dev)
     sum_launches = batch.last_launch_count()
+    # ---- two more fused consumers: ground-station visibility and closest approach ----
+    jd_np, fr_np = np.asarray(jd), np.asarray(fr)
+    stations = [(np.radians(40.0), np.radians(-105.0), 1.6, np.radians(10.0)),
+                (0.0, np.radians(30.0), 0.0, np.radians(5.0)),
+                (np.radians(78.2), np.radians(15.4), 0.4, np.radians(5.0)),
+                (np.radians(-33.9), np.radians(151.2), 0.05, np.radians(10.0))]
+    vis, _ = batch.propagate_visibility(jd_np, fr_np, stations)  # warm-up: scratch
+    if dist is not None:
+        dist.barrier()
+    tv = time.perf_counter()
+    for _ in range(e2e_steps):
+        vis, _ = batch.propagate_visibility(jd_np, fr_np, stations)  # host in, host out
+    vis_s = pb.max_over_ranks(time.perf_counter() - tv, dist, dev)
+    prim_idx = [0, n // 3, (2 * n) // 3, n - 1]
+    d_prim = torch.empty((6, len(prim_idx), m), dtype=torch.float64, device=dev)
+    d_perr = torch.empty((len(prim_idx), m), dtype=torch.int32, device=dev)
+    sub = (pb.capi.Tle * len(prim_idx))(*[tles[i] for i in prim_idx])
+    prim_batch = pb.SatelliteBatch.from_parsed(sub, pb.WGS72, "i", device=local)
+    prim_batch.propagate(torch.tensor(jd_np, device=dev), torch.tensor(fr_np, device=dev), d_prim, d_perr)
+    prim_batch.close()
+    primaries = np.ascontiguousarray(d_prim[0:3].permute(1, 0, 2).cpu().numpy())
+    prox = batch.propagate_proximity(jd_np, fr_np, primaries, 200.0)  # warm-up
+    if dist is not None:
+        dist.barrier()
+    tp = time.perf_counter()
+    for _ in range(e2e_steps):
+        prox = batch.propagate_proximity(jd_np, fr_np, primaries, 200.0)
+    prox_s = pb.max_over_ranks(time.perf_counter() - tp, dist, dev)
+    screens = {
+        "e2e_visibility": {
+            "value": float(n) * m * world * e2e_steps / vis_s, "unit": "evals/s",
+            "what": "perturb_gpu_propagate_visibility: host time grid in, per (satellite, station) "
+                    "pass summaries out, %d stations, elevation masks 5-10 deg" % len(stations),
+            "h2d_bytes_per_step": int(2 * m * 8 + 32 * len(stations)),
+            "d2h_bytes_per_step": int(n * len(stations) * 32), "steps": e2e_steps,
+            "visible_fraction": float(vis["n_visible"].sum()) / (float(n) * m * len(stations)),
+            "passes": int(vis["n_passes"].sum()),
+        },
+        "e2e_proximity": {
+            "value": float(n) * m * world * e2e_steps / prox_s, "unit": "evals/s",
+            "what": "perturb_gpu_propagate_proximity: host time grid and %d primaries' positions in, "
+                    "per (satellite, primary) closest approach out, threshold 200 km" % len(prim_idx),
+            "h2d_bytes_per_step": int(2 * m * 8 + primaries.nbytes),
+            "d2h_bytes_per_step": int(n * len(prim_idx) * 16), "steps": e2e_steps,
+            "pairs_below_threshold": int((prox["n_below"] > 0).sum()),
+        },
+    }
     batch.close()
     torch.cuda.empty_cache()
     # ---- the drop-in call itself: C++ user code, std::vector destinations (one process per GPU)
@@ -728,6 +775,8 @@ def run_gpu(args):
             "launches_per_step": int(sum_launches),
             "ok_fraction": float(summ["n_ok"].sum()) / (float(n) * m),
         },
+        "e2e_visibility": screens["e2e_visibility"],
+        "e2e_proximity": screens["e2e_proximity"],
         "workloads": workloads,
         "inproc_sharded": inproc,
         "gpu_launches": int(launches_per_step * args.steps),

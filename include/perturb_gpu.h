@@ -186,7 +186,9 @@ int perturb_gpu_propagate_into(perturb_gpu_batch *batch, const double *jd, const
  * (Earth radii, -, rad, rad, rad, rad, rad/min). They are written when the reference writes
  * them (codes 0, 3, 4, 6) and are quiet NaN otherwise (codes 1 and 2 return before the store).
  * jd_frac == NULL selects the `propagate_from_epoch` form with `jd` holding minutes.
- * All output buffers of this entry point must be DEVICE memory. */
+ * posvel, err and elements are all device memory (asynchronous, written by the kernel) or all
+ * host memory (time-chunked through device buffers of the call; returns when the results are
+ * in place). */
 int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
                                    const double *jd_frac, size_t m, double *posvel,
                                    int32_t *err, double *elements, size_t row_stride,
@@ -217,6 +219,64 @@ typedef struct perturb_gpu_summary {
 int perturb_gpu_propagate_summary(perturb_gpu_batch *batch, const double *jd,
                                   const double *jd_frac, size_t m, perturb_gpu_summary *out,
                                   void *stream);
+
+/* Fused consumer: ground-station visibility screen. Equivalent to running
+ * `sat.propagate(JulianDate(jd[k], jd_frac[k]), sv)` for every satellite and time, rotating
+ * sv.position from TEME into the Earth-fixed frame by the sidereal angle the reference's
+ * gstime_SGP4(jd + jd_frac) gives (src/sgp4.cpp:2506-2525; polar motion ignored), and testing
+ * the elevation seen from each station against its mask -- without materialising the states.
+ * Evaluations that do not return NONE count as not visible. Per (satellite, station):
+ *   n_visible          grid times at or above the mask
+ *   n_passes           maximal runs of consecutive visible times
+ *   k_first_rise       first visible index (-1 if none), k_last_visible likewise the last
+ *   max_sin_elevation  largest sin(elevation) over all NONE evaluations, visible or not, and
+ *   k_max_elevation    the lowest k attaining it (-inf / -1 if no evaluation returned NONE)
+ * and, if `passes` is not NULL, the first `max_passes` passes as (rise index, set index) pairs
+ * (set = last visible index of the pass; unused slots -1):
+ *   passes[((i * n_stations + s) * max_passes + j) * 2 + {0, 1}]
+ * `out` [n][n_stations] and `passes` may be host or device memory (both the same); stations
+ * [n_stations <= 64] is HOST memory. Station positions are geodetic on the ellipsoid of the
+ * batch's gravity model (flattening 1/298.26 for WGS-72, 1/298.257223563 for WGS-84). */
+typedef struct perturb_gpu_station {
+    double latitude_rad, longitude_rad, altitude_km, min_elevation_rad;
+} perturb_gpu_station;
+
+typedef struct perturb_gpu_pass_summary {
+    double max_sin_elevation;
+    int32_t k_max_elevation;
+    int32_t n_visible;
+    int32_t n_passes;
+    int32_t k_first_rise;
+    int32_t k_last_visible;
+    int32_t reserved;
+} perturb_gpu_pass_summary;
+
+int perturb_gpu_propagate_visibility(perturb_gpu_batch *batch, const double *jd,
+                                     const double *jd_frac, size_t m,
+                                     const perturb_gpu_station *stations, size_t n_stations,
+                                     perturb_gpu_pass_summary *out, int32_t *passes,
+                                     size_t max_passes, void *stream);
+
+/* Fused consumer: closest approach to a few primary objects (conjunction pre-filter). For every
+ * satellite i and primary p, over the evaluations that return NONE:
+ *   d_min_km  smallest |sv.position - primary_p(k)| and k_min, the lowest k attaining it
+ *             (+inf / -1 if there is none)
+ *   n_below   number of grid times closer than threshold_km
+ * primaries: TEME positions [km] of the primaries ON THE SAME GRID, three planes per primary,
+ *   primaries[(p * 3 + c) * m + k], c = x, y, z   (host or device memory; e.g. the position
+ *   planes a perturb_gpu_propagate call wrote for a batch of the primaries; NaN = no state);
+ * out [n][n_primaries] host or device memory, n_primaries <= 64. jd_frac == NULL selects the
+ * `propagate_from_epoch` form with `jd` holding minutes. */
+typedef struct perturb_gpu_approach {
+    double d_min_km;
+    int32_t k_min;
+    int32_t n_below;
+} perturb_gpu_approach;
+
+int perturb_gpu_propagate_proximity(perturb_gpu_batch *batch, const double *jd,
+                                    const double *jd_frac, size_t m, const double *primaries,
+                                    size_t n_primaries, double threshold_km,
+                                    perturb_gpu_approach *out, void *stream);
 
 /* Replaces `ClassicalOrbitalElements(StateVector, GravModel)` (src/perturb.cpp:119-131, i.e.
  * sgp4::rv2coe_SGP4, src/sgp4.cpp:2863-3064) for every state of a propagate result -- what the

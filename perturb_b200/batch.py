@@ -357,10 +357,22 @@ class SatelliteBatch:
             self.synchronize()
         return states, err
 
-    def propagate_elements(self, jd, jd_frac=None, stream=None):
+    def propagate_elements(self, jd, jd_frac=None, stream=None, host=False):
         """propagate (or propagate_from_epoch when jd_frac is None, jd = minutes) that also
         returns the mean elements sgp4() leaves in sat_rec: (posvel [6,n,m], err [n,m],
-        elements [7,n,m] = am, em, im, Om, om, mm, nm), all as torch CUDA tensors."""
+        elements [7,n,m] = am, em, im, Om, om, mm, nm), all as torch CUDA tensors -- or, with
+        host=True, as numpy arrays filled through the C ABI's host-buffer path."""
+        if host:
+            jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
+            m = int(jd.shape[0])
+            posvel = np.empty((6, self.n, m))
+            elements = np.empty((7, self.n, m))
+            err = np.empty((self.n, m), dtype=np.int32)
+            st = capi.lib().perturb_gpu_propagate_elements(
+                self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(posvel), _ptr(err), _ptr(elements),
+                max(m, 1), max(self.n * m, 1), stream)
+            capi.check(st, "perturb_gpu_propagate_elements")
+            return posvel, err, elements
         import torch
         dev = torch.device("cuda", capi.lib().perturb_gpu_device(self._h))
         m = int(jd.shape[0])
@@ -400,6 +412,51 @@ class SatelliteBatch:
         st = capi.lib().perturb_gpu_propagate_summary(
             self._h, _ptr(jd), _ptr(jd_frac), int(jd.shape[0]), out.data_ptr(), stream)
         capi.check(st, "perturb_gpu_propagate_summary")
+
+    STATION_DTYPE = np.dtype([("latitude_rad", "f8"), ("longitude_rad", "f8"), ("altitude_km", "f8"),
+                              ("min_elevation_rad", "f8")])
+    PASS_DTYPE = np.dtype([("max_sin_elevation", "f8"), ("k_max_elevation", "i4"), ("n_visible", "i4"),
+                           ("n_passes", "i4"), ("k_first_rise", "i4"), ("k_last_visible", "i4"),
+                           ("reserved", "i4")])
+    APPROACH_DTYPE = np.dtype([("d_min_km", "f8"), ("k_min", "i4"), ("n_below", "i4")])
+
+    def propagate_visibility(self, jd, jd_frac, stations, max_passes=0, stream=None):
+        """Fused ground-station visibility screen (perturb_gpu_propagate_visibility): `stations`
+        is a sequence of (latitude_rad, longitude_rad, altitude_km, min_elevation_rad). Returns
+        (summary [n, S] PASS_DTYPE, passes [n, S, max_passes, 2] int32 or None) without
+        materialising the [n, m] states."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
+        st_arr = np.zeros(len(stations), dtype=self.STATION_DTYPE)
+        for j, row in enumerate(stations):
+            st_arr[j] = tuple(float(x) for x in row)
+        out = np.zeros((self.n, len(stations)), dtype=self.PASS_DTYPE)
+        passes = np.zeros((self.n, len(stations), max_passes, 2), dtype=np.int32) if max_passes else None
+        st = capi.lib().perturb_gpu_propagate_visibility(
+            self._h, _ptr(jd), _ptr(jd_frac), int(jd.shape[0]), st_arr.ctypes.data, len(stations),
+            out.ctypes.data, _ptr(passes), int(max_passes), stream)
+        capi.check(st, "perturb_gpu_propagate_visibility")
+        self.synchronize()
+        return out, passes
+
+    def propagate_proximity(self, jd, jd_frac, primaries, threshold_km, stream=None):
+        """Fused closest-approach screen (perturb_gpu_propagate_proximity): `primaries` [P, 3, m]
+        float64 TEME positions on the same grid (numpy, or a CUDA tensor on the batch's device).
+        Returns [n, P] APPROACH_DTYPE. jd_frac None: jd = minutes."""
+        jd, jd_frac = _times(jd, "jd"), _times(jd_frac, "jd_frac")
+        m = int(jd.shape[0])
+        if isinstance(primaries, np.ndarray):
+            primaries = np.ascontiguousarray(primaries, dtype=np.float64)
+        _check_output(primaries, "primaries", "float64", (1, 3, m))
+        if tuple(primaries.shape[1:]) != (3, m) or _elem_strides(primaries) != [3 * m, m, 1]:
+            raise ValueError("primaries must be a contiguous [P, 3, m] array")
+        n_prim = int(primaries.shape[0])
+        out = np.zeros((self.n, n_prim), dtype=self.APPROACH_DTYPE)
+        st = capi.lib().perturb_gpu_propagate_proximity(
+            self._h, _ptr(jd), _ptr(jd_frac), m, _ptr(primaries), n_prim, float(threshold_km),
+            out.ctypes.data, stream)
+        capi.check(st, "perturb_gpu_propagate_proximity")
+        self.synchronize()
+        return out
 
     def propagate_into(self, jd, jd_frac, states, err=None):
         """The drop-in loop `errs[i, k] = sats[i].propagate(times[k], svs[i, k])` into the

@@ -37,7 +37,7 @@ EXPORTS = (
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles perturb_gpu_parse_tle "
     "perturb_gpu_propagate_into perturb_gpu_elsetrec_size perturb_gpu_export_records "
-    "perturb_gpu_write_back"
+    "perturb_gpu_write_back perturb_gpu_propagate_visibility perturb_gpu_propagate_proximity"
 ).split()
 # ... and include/perturb_benchtools.h + include/perturb_synth.h (libperturb_benchtools.so)
 TOOLS_EXPORTS = (
@@ -113,6 +113,10 @@ def lib():
         L.perturb_gpu_propagate_into.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
         L.perturb_gpu_export_records.argtypes = [vp, vp, C.c_size_t]
         L.perturb_gpu_write_back.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, C.c_size_t]
+        L.perturb_gpu_propagate_visibility.argtypes = [
+            vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_size_t, vp]
+        L.perturb_gpu_propagate_proximity.argtypes = [
+            vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_double, vp, vp]
     except AttributeError:
         # an older comparison build loaded through PERTURB_GPU_LIB (kernel sweeps only)
         if "PERTURB_GPU_LIB" not in os.environ:

@@ -523,6 +523,26 @@ void fill_launch(const perturb_gpu_batch *b, pb::PropLaunch &l) {
     l.res_cnt = b->d_res_cnt;
     l.res_range = b->d_res_range;
     l.res_cap = b->res_cap;
+    l.stations = nullptr;
+    l.n_stations = 0;
+    l.gmst = nullptr;
+    l.vis_words = nullptr;
+    l.vis_best = nullptr;
+    l.pass_out = nullptr;
+    l.passes = nullptr;
+    l.max_passes = 0;
+    l.primaries = nullptr;
+    l.n_primaries = 0;
+    l.threshold_km = 0.0;
+    l.prox_partials = nullptr;
+    l.approach_out = nullptr;
+    l.out = nullptr;
+    l.err = nullptr;
+    l.states = nullptr;
+    l.elements = nullptr;
+    l.summary_partials = nullptr;
+    l.summary_out = nullptr;
+    l.plane_stride = l.row_stride = l.err_row_stride = 0;
     l.fork = b->ev_fork;
     l.fork_recorded = false;
     for (int c = 0; c < PB_CLS_COUNT; ++c) {
@@ -903,8 +923,59 @@ int perturb_gpu_propagate_elements(perturb_gpu_batch *batch, const double *jd,
                                    int32_t *err, double *elements, size_t row_stride,
                                    size_t plane_stride, void *stream) {
     if (elements == nullptr) return fail(PERTURB_GPU_ERR_ARG, "elements is null");
-    return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m, posvel, err, row_stride,
-                          plane_stride, stream, elements);
+    if (batch == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    const bool all_dev = is_device_pointer(elements) && is_device_pointer(posvel) && is_device_pointer(err);
+    if (all_dev || m == 0 || batch->n == 0) {
+        return propagate_impl(batch, jd, jd_frac, jd_frac != nullptr, m, posvel, err, row_stride,
+                              plane_stride, stream, elements);
+    }
+    if (is_device_pointer(elements) || is_device_pointer(posvel) || is_device_pointer(err)) {
+        return fail(PERTURB_GPU_ERR_ARG, "posvel, err and elements must all be host or all be device memory");
+    }
+    if (posvel == nullptr || err == nullptr || jd == nullptr || row_stride < m ||
+        plane_stride < batch->n * row_stride) {
+        return fail(PERTURB_GPU_ERR_ARG, "null pointer, row_stride < m or plane_stride < n * row_stride");
+    }
+    // Host outputs: time-chunks through device buffers of this call (13 planes + codes, at most
+    // ~256 MiB), copied out plane by plane; returns when the results are in place.
+    DeviceGuard guard(batch->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    const size_t n = batch->n;
+    const size_t per_time = n * (13 * sizeof(double) + sizeof(int32_t));
+    size_t mc = std::max<size_t>(2, (static_cast<size_t>(256) << 20) / per_time) & ~static_cast<size_t>(1);
+    mc = std::min(mc, (m + 1) & ~static_cast<size_t>(1));
+    ScratchFree scratch;  // [0] posvel + elements planes, [1] codes, [2] time grid
+    PB_CUDA(cudaMalloc(&scratch.p[0], 13 * n * mc * sizeof(double)));
+    PB_CUDA(cudaMalloc(&scratch.p[1], n * mc * sizeof(int32_t)));
+    PB_CUDA(cudaMalloc(&scratch.p[2], 2 * m * sizeof(double)));
+    double *d_pv = static_cast<double *>(scratch.p[0]);
+    double *d_el = d_pv + 6 * n * mc;
+    int32_t *d_err = static_cast<int32_t *>(scratch.p[1]);
+    double *d_ta = static_cast<double *>(scratch.p[2]), *d_tb = d_ta + m;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PB_CUDA(cudaMemcpyAsync(d_ta, jd, m * sizeof(double), cudaMemcpyDefault, s));
+    if (jd_frac != nullptr) {
+        PB_CUDA(cudaMemcpyAsync(d_tb, jd_frac, m * sizeof(double), cudaMemcpyDefault, s));
+    }
+    int launches = 0;
+    for (size_t k0 = 0; k0 < m; k0 += mc) {
+        const size_t mk = std::min(mc, m - k0);
+        const int st = propagate_impl(batch, d_ta + k0, jd_frac != nullptr ? d_tb + k0 : nullptr,
+                                      jd_frac != nullptr, mk, d_pv, d_err, mc, n * mc, stream, d_el);
+        if (st != PERTURB_GPU_OK) return st;
+        launches += batch->last_launches;
+        for (int pl = 0; pl < 13; ++pl) {
+            double *dst = (pl < 6 ? posvel + pl * plane_stride : elements + (pl - 6) * plane_stride) + k0;
+            PB_CUDA(cudaMemcpy2DAsync(dst, row_stride * sizeof(double), d_pv + pl * n * mc,
+                                      mc * sizeof(double), mk * sizeof(double), n,
+                                      cudaMemcpyDeviceToHost, s));
+        }
+        PB_CUDA(cudaMemcpy2DAsync(err + k0, row_stride * sizeof(int32_t), d_err, mc * sizeof(int32_t),
+                                  mk * sizeof(int32_t), n, cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+    }
+    batch->last_launches = launches;
+    return PERTURB_GPU_OK;
 }
 
 int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const double *jd_frac,
@@ -979,6 +1050,214 @@ int perturb_gpu_propagate_summary(perturb_gpu_batch *b, const double *jd, const 
         PB_CUDA(cudaMemcpyAsync(out, folded, b->n * sizeof(perturb_gpu_summary),
                                 cudaMemcpyDeviceToHost, stream));
     }
+    return PERTURB_GPU_OK;
+}
+
+namespace {
+
+// The handle's general device scratch (shared by the fused consumers; one call at a time).
+int ensure_scratch(perturb_gpu_batch *b, size_t bytes) {
+    if (b->summary_cap >= bytes) return PERTURB_GPU_OK;
+    cudaFree(b->d_summary);
+    b->d_summary = nullptr;
+    b->summary_cap = 0;
+    PB_CUDA(cudaMalloc(&b->d_summary, bytes));
+    b->summary_cap = bytes;
+    return PERTURB_GPU_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// Time grid of a fused-consumer call on the device (copies host grids into the handle's buffer).
+int stage_times(perturb_gpu_batch *b, const double *jd, const double *jd_frac, size_t m,
+                cudaStream_t stream, const double **d_ta, const double **d_tb) {
+    const bool use_jd = jd_frac != nullptr;
+    *d_ta = jd;
+    *d_tb = jd_frac;
+    const bool ta_dev = is_local_device_pointer(jd, b->device);
+    const bool tb_dev = use_jd ? is_local_device_pointer(jd_frac, b->device) : true;
+    if (ta_dev && tb_dev) return PERTURB_GPU_OK;
+    const int st = ensure_times(b, m);
+    if (st != PERTURB_GPU_OK) return st;
+    if (!ta_dev) {
+        PB_CUDA(cudaMemcpyAsync(b->d_times, jd, m * sizeof(double), cudaMemcpyDefault, stream));
+        *d_ta = b->d_times;
+    }
+    if (use_jd && !tb_dev) {
+        PB_CUDA(cudaMemcpyAsync(b->d_times + m, jd_frac, m * sizeof(double), cudaMemcpyDefault,
+                                stream));
+        *d_tb = b->d_times + m;
+    }
+    return PERTURB_GPU_OK;
+}
+
+}  // namespace
+
+int perturb_gpu_propagate_visibility(perturb_gpu_batch *b, const double *jd,
+                                     const double *jd_frac, size_t m,
+                                     const perturb_gpu_station *stations, size_t n_stations,
+                                     perturb_gpu_pass_summary *out, int32_t *passes,
+                                     size_t max_passes, void *stream_arg) {
+    static_assert(sizeof(perturb_gpu_pass_summary) == 32, "pass summary is 32 bytes");
+    if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    b->last_launches = 0;
+    if (b->n == 0 || n_stations == 0) return PERTURB_GPU_OK;
+    if (jd == nullptr || jd_frac == nullptr || stations == nullptr || out == nullptr || m == 0 ||
+        m > (static_cast<size_t>(1) << 30) || n_stations > 64 || max_passes > 4096 ||
+        (passes != nullptr && max_passes == 0)) {
+        return fail(PERTURB_GPU_ERR_ARG, "visibility: null pointer, empty / oversized grid, more than "
+                                         "64 stations, or passes without max_passes");
+    }
+    if (is_device_pointer(stations)) return fail(PERTURB_GPU_ERR_ARG, "stations must be host memory");
+    const bool out_dev = is_device_pointer(out);
+    if (passes != nullptr && is_device_pointer(passes) != out_dev) {
+        return fail(PERTURB_GPU_ERR_ARG, "out and passes must both be host or both be device memory");
+    }
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_arg);
+    b->last_stream = stream;
+    PB_CUDA(cudaStreamWaitEvent(stream, b->ev_call, 0));
+    const double *d_ta, *d_tb;
+    int st = stage_times(b, jd, jd_frac, m, stream, &d_ta, &d_tb);
+    if (st != PERTURB_GPU_OK) return st;
+
+    // stations on the ellipsoid of the batch's gravity model -> Earth-fixed position + zenith
+    const double flat = (b->grav.radiusearthkm == 6378.137) ? 1.0 / 298.257223563 : 1.0 / 298.26;
+    const double e2 = flat * (2.0 - flat), a = b->grav.radiusearthkm;
+    std::vector<double> packed(8 * n_stations);
+    for (size_t s = 0; s < n_stations; ++s) {
+        const double sl = std::sin(stations[s].latitude_rad), cl = std::cos(stations[s].latitude_rad);
+        const double so = std::sin(stations[s].longitude_rad), co = std::cos(stations[s].longitude_rad);
+        const double nn = a / std::sqrt(1.0 - e2 * sl * sl), h = stations[s].altitude_km;
+        double *q = &packed[8 * s];
+        q[0] = (nn + h) * cl * co;
+        q[1] = (nn + h) * cl * so;
+        q[2] = (nn * (1.0 - e2) + h) * sl;
+        q[3] = cl * co;
+        q[4] = cl * so;
+        q[5] = sl;
+        q[6] = std::sin(stations[s].min_elevation_rad);
+        q[7] = 0.0;
+    }
+    const size_t chunks = pb::summary_chunks(m), pairs = b->n * n_stations;
+    const size_t o_st = 0, o_gm = align256(o_st + packed.size() * sizeof(double));
+    const size_t o_words = align256(o_gm + 2 * m * sizeof(double));
+    const size_t o_best = align256(o_words + pairs * chunks * sizeof(uint32_t));
+    const size_t o_out = align256(o_best + pairs * chunks * sizeof(double2));
+    const size_t o_pass = align256(o_out + pairs * sizeof(perturb_gpu_pass_summary));
+    const size_t total = o_pass + (out_dev ? 0 : pairs * max_passes * 2 * sizeof(int32_t));
+    st = ensure_scratch(b, total);
+    if (st != PERTURB_GPU_OK) return st;
+    char *base = static_cast<char *>(b->d_summary);
+    PB_CUDA(cudaMemcpyAsync(base + o_st, packed.data(), packed.size() * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));  // (pageable source: staged before return)
+    if (out_dev) {
+        st = peer_ready(b, pointer_device(out));
+        if (st != PERTURB_GPU_OK) return st;
+    }
+    pb::launch_gmst(d_ta, d_tb, static_cast<int>(m), reinterpret_cast<double *>(base + o_gm), stream);
+    PB_CUDA(cudaGetLastError());
+
+    pb::PropLaunch l;
+    fill_launch(b, l);
+    l.use_jd = 1;
+    l.ta = d_ta;
+    l.tb = d_tb;
+    l.m = static_cast<int>(m);
+    l.n = b->n;
+    l.stations = reinterpret_cast<const double *>(base + o_st);
+    l.n_stations = static_cast<int>(n_stations);
+    l.gmst = reinterpret_cast<const double *>(base + o_gm);
+    l.vis_words = reinterpret_cast<uint32_t *>(base + o_words);
+    l.vis_best = reinterpret_cast<double2 *>(base + o_best);
+    l.pass_out = out_dev ? static_cast<void *>(out) : static_cast<void *>(base + o_out);
+    l.passes = (passes == nullptr) ? nullptr
+               : out_dev           ? passes
+                                   : reinterpret_cast<int32_t *>(base + o_pass);
+    l.max_passes = static_cast<int>(max_passes);
+    const int launched = pb::launch_sgp4_propagate(l, stream);
+    if (launched < 0) {
+        return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+    }
+    b->last_launches = launched + 1;
+    PB_CUDA(cudaGetLastError());
+    if (!out_dev) {
+        PB_CUDA(cudaMemcpyAsync(out, base + o_out, pairs * sizeof(perturb_gpu_pass_summary),
+                                cudaMemcpyDeviceToHost, stream));
+        if (passes != nullptr) {
+            PB_CUDA(cudaMemcpyAsync(passes, base + o_pass, pairs * max_passes * 2 * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    PB_CUDA(cudaEventRecord(b->ev_call, stream));
+    return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_propagate_proximity(perturb_gpu_batch *b, const double *jd, const double *jd_frac,
+                                    size_t m, const double *primaries, size_t n_primaries,
+                                    double threshold_km, perturb_gpu_approach *out,
+                                    void *stream_arg) {
+    static_assert(sizeof(perturb_gpu_approach) == 16, "approach record is 16 bytes");
+    if (b == nullptr) return fail(PERTURB_GPU_ERR_ARG, "batch is null");
+    b->last_launches = 0;
+    if (b->n == 0 || n_primaries == 0) return PERTURB_GPU_OK;
+    if (jd == nullptr || primaries == nullptr || out == nullptr || m == 0 ||
+        m > (static_cast<size_t>(1) << 30) || n_primaries > 64 || !(threshold_km >= 0.0)) {
+        return fail(PERTURB_GPU_ERR_ARG, "proximity: null pointer, empty / oversized grid, more than "
+                                         "64 primaries or a negative threshold");
+    }
+    const bool out_dev = is_device_pointer(out);
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(PERTURB_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_arg);
+    b->last_stream = stream;
+    PB_CUDA(cudaStreamWaitEvent(stream, b->ev_call, 0));
+    const double *d_ta, *d_tb;
+    int st = stage_times(b, jd, jd_frac, m, stream, &d_ta, &d_tb);
+    if (st != PERTURB_GPU_OK) return st;
+
+    const bool prim_dev = is_local_device_pointer(primaries, b->device);
+    const size_t chunks = pb::summary_chunks(m), pairs = b->n * n_primaries;
+    const size_t prim_bytes = n_primaries * 3 * m * sizeof(double);
+    const size_t o_prim = 0, o_part = align256(prim_dev ? 0 : prim_bytes);
+    const size_t o_out = align256(o_part + pairs * chunks * pb::prox_partial_bytes());
+    const size_t total = o_out + (out_dev ? 0 : pairs * sizeof(perturb_gpu_approach));
+    st = ensure_scratch(b, total);
+    if (st != PERTURB_GPU_OK) return st;
+    char *base = static_cast<char *>(b->d_summary);
+    const double *d_prim = primaries;
+    if (!prim_dev) {
+        PB_CUDA(cudaMemcpyAsync(base + o_prim, primaries, prim_bytes, cudaMemcpyDefault, stream));
+        d_prim = reinterpret_cast<const double *>(base + o_prim);
+    }
+    if (out_dev) {
+        st = peer_ready(b, pointer_device(out));
+        if (st != PERTURB_GPU_OK) return st;
+    }
+    pb::PropLaunch l;
+    fill_launch(b, l);
+    l.use_jd = jd_frac != nullptr ? 1 : 0;
+    l.ta = d_ta;
+    l.tb = d_tb;
+    l.m = static_cast<int>(m);
+    l.n = b->n;
+    l.primaries = d_prim;
+    l.n_primaries = static_cast<int>(n_primaries);
+    l.threshold_km = threshold_km;
+    l.prox_partials = base + o_part;
+    l.approach_out = out_dev ? static_cast<void *>(out) : static_cast<void *>(base + o_out);
+    const int launched = pb::launch_sgp4_propagate(l, stream);
+    if (launched < 0) {
+        return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+    }
+    b->last_launches = launched;
+    PB_CUDA(cudaGetLastError());
+    if (!out_dev) {
+        PB_CUDA(cudaMemcpyAsync(out, base + o_out, pairs * sizeof(perturb_gpu_approach),
+                                cudaMemcpyDeviceToHost, stream));
+    }
+    PB_CUDA(cudaEventRecord(b->ev_call, stream));
     return PERTURB_GPU_OK;
 }
 

@@ -57,6 +57,27 @@ struct PropLaunch {
     double *elements;  // optional 7 planes am, em, im, Om, om, mm, nm (same strides as out)
     // array-of-StateVector mode (out unused): 8 doubles per record at (sat * row_stride + k)
     double *states;
+    // fused visibility screen (out/err unused): stations [S][8] doubles = Earth-fixed position
+    // x, y, z [km], unit zenith ux, uy, uz, sin(minimum elevation), unused; gmst [m][2] = sin,
+    // cos of the sidereal angle; scratch vis_words [n][S][chunks] (one bit per time), vis_best
+    // [n][S][chunks] {largest sin(elevation), its time index}; results pass_out [n][S]
+    // (perturb_gpu_pass_summary), passes [n][S][max_passes][2] or null
+    const double *stations;
+    int n_stations;
+    const double *gmst;
+    uint32_t *vis_words;
+    double2 *vis_best;
+    void *pass_out;
+    int32_t *passes;
+    int max_passes;
+    // fused proximity screen: primaries [P][3][m] TEME km; scratch prox_partials [n][P][chunks]
+    // {smallest squared distance, its time index, count below the threshold}; results
+    // approach_out [n][P] (perturb_gpu_approach)
+    const double *primaries;
+    int n_primaries;
+    double threshold_km;
+    void *prox_partials;
+    void *approach_out;
     // fused summary mode (out/err unused): partials [n][chunks], then summary [n]
     void *summary_partials;  // perturb_gpu_summary [n * summary_chunks], scratch
     void *summary_out;       // perturb_gpu_summary [n]
@@ -93,8 +114,15 @@ enum {
 void launch_write_back(const PropLaunch &l, const uint8_t *d_cls, double ta, double tb,
                        double *d_wb, cudaStream_t stream);
 
+// (sin, cos) of gstime_SGP4(jd[k] + jd_frac[k]) -> d_sincos[2 k], [2 k + 1].
+void launch_gmst(const double *d_jd, const double *d_jd_frac, int m, double *d_sincos,
+                 cudaStream_t stream);
+
 // Number of per-satellite partial records the summary mode needs for a grid of m times.
 size_t summary_chunks(size_t m);
+
+// sizeof the proximity screen's per-chunk partial record.
+size_t prox_partial_bytes();
 
 }  // namespace pb
 

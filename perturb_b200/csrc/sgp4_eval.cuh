@@ -619,11 +619,13 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     double sineo1, coseo1;
     if (UNIFORM && PB_KEPLER_SMALL) {
         const bool small = el2 < kMc[MC_KEPLER_SMALL];
-        if (__all_sync(0xffffffffu, small)) {
+        // ONE vote: both branch decisions below derive from the same warp-uniform mask
+        const unsigned small_lanes = __ballot_sync(0xffffffffu, small);
+        if (small_lanes == 0xffffffffu) {
             kepler_small(u, axnl, aynl, sineo1, coseo1);
         } else {
             kepler_newton<true>(u, axnl, aynl, sineo1, coseo1);
-            if (__any_sync(0xffffffffu, small)) {
+            if (small_lanes != 0u) {
                 double sf, cf;
                 kepler_small(u, axnl, aynl, sf, cf);
                 sineo1 = small ? sf : sineo1;

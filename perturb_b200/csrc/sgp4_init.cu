@@ -132,6 +132,28 @@ pack_kernel(const double *__restrict__ stage, int n, const int32_t *__restrict__
 
 }  // namespace
 
+// Pre-pass of the visibility screen: (sin, cos) of the Greenwich mean sidereal angle of every
+// grid time, theta = gstime_SGP4(jd + jd_frac) (src/sgp4.cpp:2506-2525; the rotation about z
+// that takes TEME to the Earth-fixed frame, polar motion ignored). In this translation unit
+// (-fmad=false) the angle is the reference formula's double bit for bit.
+__global__ void __launch_bounds__(256)
+gmst_kernel(const double *__restrict__ jd, const double *__restrict__ jd_frac, int m,
+            double *__restrict__ sincos_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const double theta = gstime_dev(jd[k] + jd_frac[k]);
+    double s, c;
+    sincos(theta, &s, &c);
+    sincos_out[2 * k] = s;
+    sincos_out[2 * k + 1] = c;
+}
+
+void launch_gmst(const double *d_jd, const double *d_jd_frac, int m, double *d_sincos,
+                 cudaStream_t stream) {
+    if (m <= 0) return;
+    gmst_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_jd, d_jd_frac, m, d_sincos);
+}
+
 void launch_sgp4init(const void *d_tles, int n, const GravAll &g, bool opsmode_a, double *d_rec,
                      double *d_pf_stage, uint8_t *d_cls, int32_t *d_init_error,
                      cudaStream_t stream) {

@@ -81,6 +81,12 @@ struct SmemConsts {  // constants of satellite `s` of the staged tile: broadcast
     }
 };
 
+struct ProxPartial {  // proximity screen, one warp's 32 times of one (satellite, primary)
+    double d2_min;  // smallest squared distance over NONE evaluations (+inf if none)
+    int k_min;      // its time index (-1 if none)
+    int n_below;    // evaluations closer than the threshold
+};
+
 struct PropParams {
     const double *pf;
     size_t n_pad;
@@ -99,6 +105,17 @@ struct PropParams {
     double *states;  // perturb_gpu_state [n][row_stride] as doubles (AoS mode)
     perturb_gpu_summary *partials;  // summary mode: [sat * chunks + chunk]
     int chunks;
+    // visibility screen
+    const double *stations;  // [S][8]
+    int n_stations;
+    const double *gmst;      // [m][2]
+    uint32_t *vis_words;     // [(sat * S + station) * chunks + chunk]
+    double2 *vis_best;       // same index: {largest sin(elevation), its time index}
+    // proximity screen
+    const double *primaries;  // [P][3][m]
+    int n_primaries;
+    double thr2;              // squared threshold [km^2]
+    ProxPartial *prox;        // [(sat * P + primary) * chunks + chunk]
     GravConsts g;
     int opsmode_a;
     int vec_ok;  // state planes and error rows allow 16-byte / 8-byte paired stores (kPair)
@@ -226,6 +243,23 @@ constexpr int kModeStates = 0;    // six state planes + error plane
 constexpr int kModeElements = 1;  // ... plus the seven mean-element planes
 constexpr int kModeSummary = 2;   // fused consumer: per-satellite envelope, no [n][m] output
 constexpr int kModeRecords = 3;   // array of 64-byte StateVector records + error plane
+constexpr int kModeVisibility = 4;  // fused consumer: ground-station visibility bits, no [n][m] output
+constexpr int kModeProximity = 5;   // fused consumer: closest approach to a few primary objects
+
+// Warp-wide minimum of non-negative doubles (they order like their bit patterns) with ties
+// going to the lowest index: three 32-bit reductions. Lanes without a candidate pass +inf, -1.
+__device__ __forceinline__ void warp_min_with_index(double &v, int &k) {
+    const unsigned full = 0xffffffffu;
+    const unsigned hi = static_cast<unsigned>(__double2hiint(v));
+    const unsigned lo = static_cast<unsigned>(__double2loint(v));
+    const unsigned m_hi = __reduce_min_sync(full, hi);
+    bool cand = hi == m_hi;
+    const unsigned m_lo = __reduce_min_sync(full, cand ? lo : 0xffffffffu);
+    cand = cand && lo == m_lo;
+    const unsigned m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(k) : 0xffffffffu);
+    v = __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo));
+    k = static_cast<int>(m_k);
+}
 
 struct LaneSummary {
     double r_min, r_max;
@@ -336,6 +370,13 @@ sgp4_prop_kernel(const PropParams p) {
     }
     const ClassFlags no_flags = {false, false, 0};
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double gm_s = 0.0, gm_c = 1.0;
+    if (MODE == kModeVisibility) {
+        static_assert(MODE != kModeVisibility || kTpl == 1, "fused screens are built for one time per lane");
+        const int kc = min(k_base + i0, p.m - 1);
+        gm_s = p.gmst[2 * kc];
+        gm_c = p.gmst[2 * kc + 1];
+    }
 
 #pragma unroll 1
     for (int s = SPLIT ? sat_first : 0; s < SATS; s += SPLIT ? sat_step : 1) {
@@ -350,10 +391,11 @@ sgp4_prop_kernel(const PropParams p) {
             nodes.count = rn.y;
             nodes.first = rn.z;
         }
-        double *row = (MODE == kModeSummary)   ? nullptr
+        constexpr bool kFused = (MODE == kModeSummary || MODE == kModeVisibility || MODE == kModeProximity);
+        double *row = kFused                   ? nullptr
                       : (MODE == kModeRecords) ? p.states + static_cast<size_t>(dst) * p.row_stride * 8
                                                : p.out + static_cast<size_t>(dst) * p.row_stride;
-        int32_t *erow = (MODE == kModeSummary) ? nullptr : p.err + static_cast<size_t>(dst) * p.err_row_stride;
+        int32_t *erow = kFused ? nullptr : p.err + static_cast<size_t>(dst) * p.err_row_stride;
         LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
                            __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
 
@@ -423,7 +465,55 @@ sgp4_prop_kernel(const PropParams p) {
                 erow_el[5 * p.plane_stride] = stored ? side.mm : nan;
                 erow_el[6 * p.plane_stride] = stored ? side.nm : nan;
             }
-            if (MODE == kModeSummary) {
+            if (MODE == kModeVisibility) {
+                // Earth-fixed position: TEME rotated about z by the sidereal angle of this
+                // lane's time (sin / cos fetched once per CTA, the lane's time never changes)
+                const bool ok = (cd == 0) && (kt < p.m);
+                const double xe = mad2(gm_c, r[0], gm_s, r[1]);
+                const double ye = msb2(gm_c, r[1], gm_s, r[0]);
+                const int word = ttile * kWarps + tgroup;
+                for (int st = 0; st < p.n_stations; ++st) {
+                    const double *q = p.stations + 8 * st;
+                    const double dx = xe - q[0], dy = ye - q[1], dz = r[2] - q[2];
+                    const double range2 = __fma_rn(dz, dz, mad2(dx, dx, dy, dy));
+                    const double up = __fma_rn(dz, q[5], mad2(dx, q[3], dy, q[4]));
+                    // sin(elevation) = up / range against the mask, without the division
+                    const double sin_el = up * rsqrt_fast(range2);
+                    const bool visible = ok && sin_el >= q[6];
+                    const unsigned bits = __ballot_sync(0xffffffffu, visible);
+                    // largest sin(elevation) of the 32 times: 1 - sin is non-negative
+                    const double gap = 1.0 - sin_el;  // (rounding can leave sin_el a hair above 1)
+                    double key = ok ? (gap > 0.0 ? gap : 0.0) : __longlong_as_double(0x7ff0000000000000LL);
+                    int kbest = ok ? kt : -1;
+                    warp_min_with_index(key, kbest);
+                    if (lane == 0) {
+                        const size_t at = (static_cast<size_t>(dst) * p.n_stations + st) * p.chunks + word;
+                        p.vis_words[at] = bits;
+                        p.vis_best[at] = make_double2(1.0 - key, static_cast<double>(kbest));
+                    }
+                }
+            } else if (MODE == kModeProximity) {
+                const bool ok = (cd == 0) && (kt < p.m);
+                const int word = ttile * kWarps + tgroup;
+                const int kc = kt < p.m ? kt : p.m - 1;
+                for (int pr = 0; pr < p.n_primaries; ++pr) {
+                    const double *q = p.primaries + static_cast<size_t>(pr) * 3 * p.m + kc;
+                    const double dx = r[0] - q[0], dy = r[1] - q[p.m], dz = r[2] - q[2 * static_cast<size_t>(p.m)];
+                    const double d2v = __fma_rn(dz, dz, mad2(dx, dx, dy, dy));
+                    const bool have = ok && (d2v == d2v);  // a primary without a state is skipped
+                    const unsigned below = __ballot_sync(0xffffffffu, have && d2v < p.thr2);
+                    double key = have ? d2v : __longlong_as_double(0x7ff0000000000000LL);
+                    int kbest = have ? kt : -1;
+                    warp_min_with_index(key, kbest);
+                    if (lane == 0) {
+                        ProxPartial out;
+                        out.d2_min = key;
+                        out.k_min = kbest;
+                        out.n_below = __popc(below);
+                        p.prox[(static_cast<size_t>(dst) * p.n_primaries + pr) * p.chunks + word] = out;
+                    }
+                }
+            } else if (MODE == kModeSummary) {
                 if (kt < p.m) {
                     if (cd == 0) {
                         const double rr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
@@ -660,6 +750,92 @@ summary_reduce_kernel(const perturb_gpu_summary *__restrict__ partials, int chun
     out[i] = r;
 }
 
+// Second pass of the visibility screen: one thread per (satellite, station) walks the visibility
+// bits in time order -- runs of ones are passes -- and folds the per-chunk elevation maxima.
+__global__ void __launch_bounds__(128)
+visibility_reduce_kernel(const uint32_t *__restrict__ words, const double2 *__restrict__ best,
+                         int chunks, int used_chunks, size_t pairs, int m,
+                         perturb_gpu_pass_summary *__restrict__ out, int32_t *__restrict__ passes,
+                         int max_passes) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= pairs) return;
+    const uint32_t *w = words + i * chunks;
+    const double2 *b = best + i * chunks;
+    int32_t *mine = passes != nullptr ? passes + i * static_cast<size_t>(max_passes) * 2 : nullptr;
+    perturb_gpu_pass_summary r;
+    r.max_sin_elevation = __longlong_as_double(0xfff0000000000000LL);
+    r.k_max_elevation = -1;
+    r.n_visible = 0;
+    r.n_passes = 0;
+    r.k_first_rise = -1;
+    r.k_last_visible = -1;
+    r.reserved = 0;
+    bool in_pass = false;
+    for (int c = 0; c < used_chunks; ++c) {
+        const double2 q = b[c];
+        if (q.y >= 0.0 && q.x > r.max_sin_elevation) {  // strict: ties stay with the earlier chunk
+            r.max_sin_elevation = q.x;
+            r.k_max_elevation = static_cast<int>(q.y);
+        }
+        const uint32_t bits = w[c];
+        r.n_visible += __popc(bits);
+        if (bits != 0u) r.k_last_visible = c * 32 + 31 - __clz(bits);
+        int pos = 0;
+        while (pos < 32) {
+            const uint32_t rest = bits >> pos;
+            if (!in_pass) {
+                if (rest == 0u) break;
+                pos += __ffs(rest) - 1;  // a rise
+                if (r.k_first_rise < 0) r.k_first_rise = c * 32 + pos;
+                if (mine != nullptr && r.n_passes < max_passes) mine[2 * r.n_passes] = c * 32 + pos;
+                r.n_passes += 1;
+                in_pass = true;
+            } else {
+                int run = __ffs(~rest) - 1;  // ones from `pos` on (zeros were shifted in on top)
+                if (run < 0) run = 32;
+                if (pos + run >= 32) break;  // the pass continues in the next chunk
+                pos += run;                   // first invisible time: the pass ended one before
+                if (mine != nullptr && r.n_passes <= max_passes) mine[2 * r.n_passes - 1] = c * 32 + pos - 1;
+                in_pass = false;
+            }
+        }
+    }
+    if (in_pass && mine != nullptr && r.n_passes <= max_passes) {
+        mine[2 * r.n_passes - 1] = m - 1;  // still above the mask at the end of the grid
+    }
+    if (mine != nullptr) {
+        for (int j = r.n_passes; j < max_passes; ++j) {
+            mine[2 * j] = -1;
+            mine[2 * j + 1] = -1;
+        }
+    }
+    out[i] = r;
+}
+
+// Second pass of the proximity screen: one thread per (satellite, primary) folds its chunk
+// partials in time order (ties to the lowest index).
+__global__ void __launch_bounds__(128)
+proximity_reduce_kernel(const ProxPartial *__restrict__ partials, int chunks, int used_chunks,
+                        size_t pairs, perturb_gpu_approach *__restrict__ out) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= pairs) return;
+    double d2 = __longlong_as_double(0x7ff0000000000000LL);
+    int k = -1, below = 0;
+    for (int c = 0; c < used_chunks; ++c) {
+        const ProxPartial q = partials[i * chunks + c];
+        if (q.k_min >= 0 && q.d2_min < d2) {
+            d2 = q.d2_min;
+            k = q.k_min;
+        }
+        below += q.n_below;
+    }
+    perturb_gpu_approach r;
+    r.d_min_km = sqrt(d2);
+    r.k_min = k;
+    r.n_below = below;
+    out[i] = r;
+}
+
 // Write-back pass: what ONE `sat.propagate(t, sv)` call leaves in
 // `Satellite::sat_rec` besides the state -- t, error, the singly averaged mean elements
 // (src/sgp4.cpp:1801-1802, 1895-1901), for deep-space satellites aycof / xlcof / con41 / x1mth2 /
@@ -720,7 +896,18 @@ void launch_class(const PropLaunch &l, PropParams p, cudaStream_t main, int &lau
             stream = main;  // could not fork: run this class in line
         }
     }
-    if (p.m <= kShortGrid) {
+    if (p.vis_words != nullptr || p.prox != nullptr) {
+        // fused screens: lanes = times, whole tiles, only the warps a single time tile fills
+        const unsigned threads = (p.n_time_tiles == 1)
+                                     ? 32u * static_cast<unsigned>((p.m + 31) / 32)
+                                     : static_cast<unsigned>(kThreads);
+        const unsigned nb = static_cast<unsigned>(blocks);
+        if (p.vis_words != nullptr) {
+            sgp4_prop_kernel<CLS, kModeVisibility><<<nb, threads, 0, stream>>>(p);
+        } else {
+            sgp4_prop_kernel<CLS, kModeProximity><<<nb, threads, 0, stream>>>(p);
+        }
+    } else if (p.m <= kShortGrid) {
         const unsigned sb = static_cast<unsigned>((tiles + kWarps - 1) / kWarps);
         if (p.partials != nullptr) {
             sgp4_prop_short_kernel<CLS, kModeSummary><<<sb, kThreads, 0, stream>>>(p, tiles);
@@ -806,6 +993,8 @@ void launch_write_back(const PropLaunch &l, const uint8_t *d_cls, double ta, dou
         l.pf, l.n_pad, l.perm, d_cls, l.n, ta, tb, l.use_jd, g, l.opsmode_a, d_wb);
 }
 
+size_t prox_partial_bytes() { return sizeof(ProxPartial); }
+
 size_t summary_chunks(size_t m) {
     return ((m + kTimeTile - 1) / kTimeTile) * kWarps;
 }
@@ -831,6 +1020,15 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     p.states = l.states;
     p.partials = static_cast<perturb_gpu_summary *>(l.summary_partials);
     p.chunks = static_cast<int>(summary_chunks(static_cast<size_t>(l.m)));
+    p.stations = l.stations;
+    p.n_stations = l.n_stations;
+    p.gmst = l.gmst;
+    p.vis_words = l.vis_words;
+    p.vis_best = l.vis_best;
+    p.primaries = l.primaries;
+    p.n_primaries = l.n_primaries;
+    p.thr2 = l.threshold_km * l.threshold_km;
+    p.prox = static_cast<ProxPartial *>(l.prox_partials);
     p.g.radiusearthkm = l.radiusearthkm;
     p.g.xke = l.xke;
     p.g.j2 = l.j2;
@@ -878,6 +1076,20 @@ int launch_sgp4_propagate(const PropLaunch &l, cudaStream_t stream) {
     launch_class<PB_CLS_DEEP_NR>(lf, p, stream, launches);
     launch_class<PB_CLS_NEAR_FULL>(lf, p, stream, launches);
     launch_class<PB_CLS_NEAR_SIMP>(lf, p, stream, launches);
+    const int used_chunks = static_cast<int>((static_cast<size_t>(l.m) + 31) / 32);
+    if (l.vis_words != nullptr && l.pass_out != nullptr && l.n > 0) {
+        const size_t pairs = l.n * static_cast<size_t>(l.n_stations);
+        visibility_reduce_kernel<<<static_cast<unsigned>((pairs + 127) / 128), 128, 0, stream>>>(
+            l.vis_words, l.vis_best, p.chunks, used_chunks, pairs, l.m,
+            static_cast<perturb_gpu_pass_summary *>(l.pass_out), l.passes, l.max_passes);
+        ++launches;
+    }
+    if (l.prox_partials != nullptr && l.approach_out != nullptr && l.n > 0) {
+        const size_t pairs = l.n * static_cast<size_t>(l.n_primaries);
+        proximity_reduce_kernel<<<static_cast<unsigned>((pairs + 127) / 128), 128, 0, stream>>>(
+            p.prox, p.chunks, used_chunks, pairs, static_cast<perturb_gpu_approach *>(l.approach_out));
+        ++launches;
+    }
     if (l.summary_partials != nullptr && l.summary_out != nullptr && l.n > 0) {
         // every (satellite, chunk) partial with chunk * 32 * kTpl < m has been written by exactly one
         // warp of exactly one class launch; all of them were joined back into `stream`

@@ -139,6 +139,17 @@ def test_calls_on_different_streams_are_ordered_per_handle():
         assert np.array_equal(_bits(o.cpu().numpy()), _bits(wo))
 
 
+def test_mean_elements_into_host_buffers_equal_the_device_ones():
+    n, m = 700, 333
+    batch = _mixed_batch(n)
+    mins = np.linspace(-300.0, 9000.0, m)
+    pv, err, el = batch.propagate_elements(mins)
+    hpv, herr, hel = batch.propagate_elements(mins, host=True)
+    assert np.array_equal(herr, err.cpu().numpy())
+    assert np.array_equal(_bits(hpv), _bits(pv.cpu().numpy()))
+    assert np.array_equal(_bits(hel), _bits(el.cpu().numpy()))
+
+
 def test_exported_records_agree_with_the_field_queries():
     n = 500
     batch = _mixed_batch(n)
