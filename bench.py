@@ -635,6 +635,7 @@ def run_gpu(args):
         dropin = dropin_harness(args.workload, local, max(2, min(args.steps, 3)))
         drop_s = pb.max_over_ranks(dropin["dropin_ms"], dist, dev) * 1e-3
         pin_s = pb.max_over_ranks(dropin["pinned_ms"], dist, dev) * 1e-3
+        reg_s = pb.max_over_ranks(dropin.get("registered_ms", 0.0), dist, dev) * 1e-3
         dn = float(dropin["satellites"]) * dropin["times"] * world
         dropin = {
             "value": dn / drop_s, "unit": "evals/s",
@@ -647,6 +648,12 @@ def run_gpu(args):
             "steps": dropin["steps"],
             "pinned_states_value": dn / pin_s if pin_s > 0 else None,
             "ratio_to_pinned_states": pin_s / drop_s if drop_s > 0 else None,
+            # the same call after `perturb::PinnedRegion pin(svs.data(), bytes)`: the vectors
+            # page-locked in place, the copy engine writes them directly (no bounce copy)
+            "registered_value": dn / reg_s if reg_s > 0 else None,
+            "registered_ratio_to_pinned_states": pin_s / reg_s if reg_s > 0 else None,
+            "register_once_ms": dropin.get("register_once_ms"),
+            "registered_equals_dropin_bit_for_bit": dropin.get("registered_equals_dropin"),
             "equals_pinned_states_bit_for_bit": dropin["dropin_equals_pinned"],
             "ok_fraction": dropin["ok_fraction"],
         }

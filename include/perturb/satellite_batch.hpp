@@ -34,6 +34,24 @@
 
 namespace perturb {
 
+/// Page-locks memory the caller already owns for the lifetime of this object (RAII over
+/// perturb_gpu_host_register / _unregister), e.g. the storage of the `std::vector<StateVector>`
+/// a propagate call fills: the copy engine then writes into it directly instead of going through
+/// bounce buffers. Construct it after the vector has its final size and destroy it before the
+/// vector is resized or freed.
+class PinnedRegion {
+public:
+    PinnedRegion(void *p, std::size_t bytes)
+        : p_(perturb_gpu_host_register(p, bytes) == PERTURB_GPU_OK ? p : nullptr) {}
+    ~PinnedRegion() { perturb_gpu_host_unregister(p_); }
+    PinnedRegion(const PinnedRegion &) = delete;
+    PinnedRegion &operator=(const PinnedRegion &) = delete;
+    bool ok() const { return p_ != nullptr; }
+
+private:
+    void *p_;
+};
+
 class SatelliteBatch {
 public:
     /// Batched `Satellite(const TwoLineElement &, GravModel)` (perturb.cpp:135-186).

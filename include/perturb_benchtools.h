@@ -33,6 +33,12 @@ int perturb_gpu_math_probe(int fn, const double *x, const double *y, double *out
 int perturb_gpu_measure_d2h(int device, size_t bytes, int reps, double *gbs_best,
                             double *gbs_mean);
 
+/* The same from ONE process over devices 0 .. n_devices-1 at once, pinned buffers allocated with
+ * `host_flags` (cudaHostAlloc flags: 0 default, 1 portable, 4 write-combined); *gbs_total = all
+ * bytes / wall time with every copy in flight together. */
+int perturb_gpu_measure_d2h_multi(int n_devices, size_t bytes, int reps, unsigned host_flags,
+                                  double *gbs_total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,8 +174,10 @@ int perturb_gpu_propagate_states(perturb_gpu_batch *batch, const double *jd,
  * the results are in place when the call returns. Chunks of the time grid are computed, copied
  * into pinned bounce buffers owned by the handle and moved into the caller's arrays by a few
  * host threads (PERTURB_GPU_HOST_THREADS, default half the hardware threads, at most 16) while
- * the next chunk is computed and copied. jd_frac == NULL selects the `propagate_from_epoch`
- * form with `jd` holding minutes. */
+ * the next chunk is computed and copied. If `states` is page-locked memory (perturb_gpu_host_alloc,
+ * or the caller's own array after perturb_gpu_host_register) the copy engine writes it directly
+ * instead; the records of failed evaluations are saved beforehand and put back. jd_frac == NULL
+ * selects the `propagate_from_epoch` form with `jd` holding minutes. */
 int perturb_gpu_propagate_into(perturb_gpu_batch *batch, const double *jd, const double *jd_frac,
                                size_t m, perturb_gpu_state *states, int32_t *err,
                                size_t row_stride);
@@ -304,6 +306,15 @@ int perturb_gpu_device_count(int *count);
  * and copy into their slices of one buffer concurrently. */
 int perturb_gpu_host_alloc(size_t bytes, void **out);
 void perturb_gpu_host_free(void *p);
+
+/* Page-locks memory the caller ALREADY owns (cudaHostRegister) -- e.g. the storage of a
+ * std::vector<StateVector> -- so that the copy engine writes results into it directly:
+ * perturb_gpu_propagate_into then needs no bounce copy (about twice the rate on a box whose host
+ * memory bandwidth bounds the bounce path). Unregister BEFORE the memory is freed or reallocated.
+ * Registering costs about as much as ten propagate calls into the same memory: worthwhile for
+ * arrays that are reused. */
+int perturb_gpu_host_register(void *p, size_t bytes);
+void perturb_gpu_host_unregister(void *p);
 
 /* Device memory for callers that do not link the CUDA runtime themselves: buffers for
  * device-resident results (and the target of a device-resident gather: shards on other GPUs

@@ -37,11 +37,13 @@ EXPORTS = (
     "perturb_gpu_record_field_count perturb_gpu_record_field_name perturb_gpu_record_field "
     "perturb_gpu_last_launch_count perturb_gpu_strerror perturb_gpu_parse_tles perturb_gpu_parse_tle "
     "perturb_gpu_propagate_into perturb_gpu_elsetrec_size perturb_gpu_export_records "
-    "perturb_gpu_write_back perturb_gpu_propagate_visibility perturb_gpu_propagate_proximity"
+    "perturb_gpu_write_back perturb_gpu_propagate_visibility perturb_gpu_propagate_proximity "
+    "perturb_gpu_host_register perturb_gpu_host_unregister"
 ).split()
 # ... and include/perturb_benchtools.h + include/perturb_synth.h (libperturb_benchtools.so)
 TOOLS_EXPORTS = (
-    "perturb_gpu_measure_fp64_peak perturb_gpu_measure_d2h perturb_gpu_math_probe "
+    "perturb_gpu_measure_fp64_peak perturb_gpu_measure_d2h perturb_gpu_measure_d2h_multi "
+    "perturb_gpu_math_probe "
     "perturb_synth_catalog perturb_synth_time_grid"
 ).split()
 
@@ -117,6 +119,9 @@ def lib():
             vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_size_t, vp]
         L.perturb_gpu_propagate_proximity.argtypes = [
             vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_double, vp, vp]
+        L.perturb_gpu_host_register.argtypes = [vp, C.c_size_t]
+        L.perturb_gpu_host_unregister.argtypes = [vp]
+        L.perturb_gpu_host_unregister.restype = None
     except AttributeError:
         # an older comparison build loaded through PERTURB_GPU_LIB (kernel sweeps only)
         if "PERTURB_GPU_LIB" not in os.environ:
@@ -136,6 +141,7 @@ def tools():
     dp = C.POINTER(C.c_double)
     T.perturb_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
     T.perturb_gpu_measure_d2h.argtypes = [C.c_int, C.c_size_t, C.c_int, dp, dp]
+    T.perturb_gpu_measure_d2h_multi.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_uint, dp]
     T.perturb_gpu_math_probe.argtypes = [C.c_int, dp, dp, dp, C.c_size_t]
     T.perturb_synth_catalog.argtypes = [
         C.c_int, C.c_size_t, C.c_uint64, C.c_char_p, C.c_char_p]

@@ -1,6 +1,9 @@
 // Host side of the C ABI (include/perturb_gpu.h): handle management, classification + sort,
 // launches, host<->device staging. C++11, no exceptions across the boundary.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -8,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -55,6 +59,41 @@ bool is_device_pointer(const void *p) {
         return false;
     }
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// memcpy for the scatter of bounce chunks into the caller's arrays: the destination is written
+// once and not read again soon, so 16-byte non-temporal stores skip the read-for-ownership a
+// cached store costs -- on a box whose host memory bandwidth is what bounds the pipeline (DMA
+// write + this copy's read and write) that is a quarter of the traffic. Falls back to memcpy for
+// destinations that are not 16-byte aligned and for the tail.
+inline void copy_streaming(void *dst, const void *src, size_t bytes) {
+#if defined(__SSE2__)
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const size_t blocks = bytes / 64;
+        const __m128i *s = static_cast<const __m128i *>(src);
+        __m128i *d = static_cast<__m128i *>(dst);
+        for (size_t i = 0; i < blocks; ++i) {
+            const __m128i a = _mm_load_si128(s + 4 * i), b = _mm_load_si128(s + 4 * i + 1);
+            const __m128i c = _mm_load_si128(s + 4 * i + 2), e = _mm_load_si128(s + 4 * i + 3);
+            _mm_stream_si128(d + 4 * i, a);
+            _mm_stream_si128(d + 4 * i + 1, b);
+            _mm_stream_si128(d + 4 * i + 2, c);
+            _mm_stream_si128(d + 4 * i + 3, e);
+        }
+        const size_t done = blocks * 64;
+        if (done < bytes) {
+            std::memcpy(static_cast<char *>(dst) + done, static_cast<const char *>(src) + done, bytes - done);
+        }
+        return;
+    }
+#endif
+    std::memcpy(dst, src, bytes);
+}
+
+inline void streaming_fence() {
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
 }
 
 // Page-locked host memory (cudaHostAlloc / cudaHostRegister): the copy engines reach it directly.
@@ -560,6 +599,128 @@ int peer_ready(perturb_gpu_batch *b, int owner) {
     return st;
 }
 
+int ensure_workers(perturb_gpu_batch *b) {
+    if (b->workers != nullptr) return PERTURB_GPU_OK;
+    unsigned threads = pb::default_host_workers();
+    if (const char *e = std::getenv("PERTURB_GPU_HOST_THREADS")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 256) threads = static_cast<unsigned>(v);
+    }
+    b->workers = new (std::nothrow) pb::HostWorkers(threads);
+    if (b->workers == nullptr) return fail(PERTURB_GPU_ERR_ALLOC, "host allocation failed");
+    return PERTURB_GPU_OK;
+}
+
+// The drop-in call into a REGISTERED (page-locked) array of StateVector records: the copy engine
+// writes the caller's memory directly, no bounce copy. The reference's untouched-on-error
+// semantics need the failed evaluations' records back as they were: per time-chunk the error
+// codes come first (small, through the handle's bounce buffer), the host saves the caller's
+// records where a code is 1-4, only then is the chunk's 2-D copy of states enqueued; saved
+// position / velocity are put back when everything has landed. `err` may be any host memory
+// or NULL.
+int propagate_into_registered(perturb_gpu_batch *b, pb::PropLaunch &l, const double *d_ta,
+                              const double *d_tb, bool use_jd, size_t m, double *states,
+                              int32_t *err, size_t row_stride, cudaStream_t stream) {
+    const size_t n = b->n;
+    size_t free_b = 0, total_b = 0;
+    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(1) << 30);  // per staging buffer
+    for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * 52);
+    size_t mc = budget / (n * 68);
+    if (mc >= 256) mc &= ~static_cast<size_t>(127);
+    mc &= ~static_cast<size_t>(1);
+    if (mc < 2) mc = 2;
+    mc = std::min(mc, (m + 1) & ~static_cast<size_t>(1));
+    const size_t nchunks = (m + mc - 1) / mc;
+    for (int i = 0; i < (nchunks > 1 ? 2 : 1); ++i) {
+        int st = ensure_stage(b, i, n * mc, 9);  // records + codes in one block
+        if (st != PERTURB_GPU_OK) return st;
+        const size_t need = n * mc * sizeof(int32_t);
+        if (b->bounce_cap[i] < need) {
+            if (b->h_bounce[i]) cudaFreeHost(b->h_bounce[i]);
+            b->h_bounce[i] = nullptr;
+            b->bounce_cap[i] = 0;
+            if (cudaHostAlloc(&b->h_bounce[i], need, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(PERTURB_GPU_ERR_ALLOC, "pinned bounce buffer allocation failed");
+            }
+            b->bounce_cap[i] = need;
+        }
+    }
+    struct Saved {
+        size_t at;  // record index i * row_stride + k
+        double pv[6];
+    };
+    std::vector<Saved> saved;
+    std::mutex saved_mu;
+    int st = ensure_workers(b);
+    if (st != PERTURB_GPU_OK) return st;
+    auto launch_chunk = [&](size_t c) -> int {
+        const int buf = static_cast<int>(c % 2);
+        const size_t k0 = c * mc, mk = std::min(mc, m - k0), ld = (mk + 1) & ~static_cast<size_t>(1);
+        if (c >= 2) PB_CUDA(cudaStreamWaitEvent(stream, b->ev_free[buf], 0));
+        l.ta = d_ta + k0;
+        l.tb = use_jd ? d_tb + k0 : nullptr;
+        l.m = static_cast<int>(mk);
+        l.out = nullptr;
+        l.states = b->d_stage[buf];
+        l.row_stride = ld;
+        l.plane_stride = n * ld;
+        l.err = reinterpret_cast<int32_t *>(b->d_stage[buf] + n * ld * 8);
+        l.err_row_stride = ld;
+        const int launched = pb::launch_sgp4_propagate(l, stream);
+        if (launched < 0) {
+            return fail(PERTURB_GPU_ERR_ARG, "satellites x times too large for one call: chunk the time grid");
+        }
+        b->last_launches += launched;
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaEventRecord(b->ev_done[buf], stream));
+        PB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
+        PB_CUDA(cudaMemcpyAsync(b->h_bounce[buf], l.err, n * ld * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, b->copy_stream));
+        PB_CUDA(cudaEventRecord(b->ev_done[buf], b->copy_stream));  // now: "codes are on the host"
+        return PERTURB_GPU_OK;
+    };
+    st = launch_chunk(0);
+    if (st != PERTURB_GPU_OK) return st;
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int buf = static_cast<int>(c % 2);
+        const size_t k0 = c * mc, mk = std::min(mc, m - k0), ld = (mk + 1) & ~static_cast<size_t>(1);
+        if (c + 1 < nchunks) {  // the next chunk computes while this one's codes are examined
+            st = launch_chunk(c + 1);
+            if (st != PERTURB_GPU_OK) return st;
+        }
+        PB_CUDA(cudaEventSynchronize(b->ev_done[buf]));
+        const int32_t *codes = static_cast<const int32_t *>(b->h_bounce[buf]);
+        b->workers->parallel_for(n, [&](size_t lo, size_t hi) {
+            std::vector<Saved> mine;
+            for (size_t i = lo; i < hi; ++i) {
+                const int32_t *ei = codes + i * ld;
+                if (err != nullptr) std::memcpy(err + i * row_stride + k0, ei, mk * sizeof(int32_t));
+                for (size_t k = 0; k < mk; ++k) {
+                    if (ei[k] != 0 && ei[k] != 6) {
+                        Saved sv;
+                        sv.at = i * row_stride + k0 + k;
+                        std::memcpy(sv.pv, states + sv.at * 8 + 2, sizeof(sv.pv));
+                        mine.push_back(sv);
+                    }
+                }
+            }
+            if (!mine.empty()) {
+                std::lock_guard<std::mutex> lock(saved_mu);
+                saved.insert(saved.end(), mine.begin(), mine.end());
+            }
+        });
+        PB_CUDA(cudaMemcpy2DAsync(states + k0 * 8, row_stride * 64, b->d_stage[buf], ld * 64, mk * 64, n,
+                                  cudaMemcpyDeviceToHost, b->copy_stream));
+        PB_CUDA(cudaEventRecord(b->ev_free[buf], b->copy_stream));
+    }
+    PB_CUDA(cudaStreamSynchronize(b->copy_stream));
+    for (const Saved &sv : saved) std::memcpy(states + sv.at * 8 + 2, sv.pv, sizeof(sv.pv));
+    PB_CUDA(cudaEventRecord(b->ev_call, stream));
+    return PERTURB_GPU_OK;
+}
+
 int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, bool use_jd,
                    size_t m, double *posvel, int32_t *err, size_t row_stride,
                    size_t plane_stride, void *stream_arg, double *elements = nullptr,
@@ -665,6 +826,14 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     // scatter into the caller's arrays while the next chunk is computed and copied (the call
     // returns when the results are in place).
     const bool direct = !keep_failed && is_pinned_host_pointer(posvel) && is_pinned_host_pointer(err);
+    if (keep_failed && is_pinned_host_pointer(posvel)) {
+        // (records in registered memory: straight DMA, failed evaluations saved and restored)
+        try {
+            return propagate_into_registered(b, l, d_ta, d_tb, use_jd, m, posvel, err, row_stride, stream);
+        } catch (const std::bad_alloc &) {
+            return fail(PERTURB_GPU_ERR_ALLOC, "host allocation failed");
+        }
+    }
     size_t free_b = 0, total_b = 0;
     PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t dpe = records ? 8 : 6;  // doubles per evaluation in the staging buffer
@@ -675,13 +844,21 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     // four chunks, so that all but the first kernel hides behind a copy; bounce chunks of
     // ~128 MiB, whole time tiles of kernel 2 where that is possible.
     const size_t total_bytes = bytes_per_eval * b->n * m;
-    if (direct && total_bytes > (static_cast<size_t>(64) << 20)) {
-        budget = std::min(budget, std::max<size_t>(total_bytes / 4, static_cast<size_t>(16) << 20));
+    if (direct && total_bytes > (static_cast<size_t>(256) << 20)) {
+        // two chunks by default: the second kernel hides behind the first copy and the row
+        // segments of the 2-D copies stay long (PERTURB_GPU_HOST_CHUNKS overrides: tuning)
+        size_t want = 2;
+        if (const char *e = std::getenv("PERTURB_GPU_HOST_CHUNKS")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) want = static_cast<size_t>(v);
+        }
+        budget = std::min(budget, std::max<size_t>((total_bytes + want - 1) / want + bytes_per_eval * b->n * 2,
+                                                   static_cast<size_t>(16) << 20));
     }
     if (!direct) budget = std::min(budget, static_cast<size_t>(128) << 20);
     const size_t m_even = (m + 1) & ~static_cast<size_t>(1);
     size_t fit = budget / (bytes_per_eval * b->n);  // times one staging buffer can hold
-    if (fit >= 256) fit &= ~static_cast<size_t>(127);
+    if (!direct && fit >= 256) fit &= ~static_cast<size_t>(127);
     fit &= ~static_cast<size_t>(1);
     if (fit < 2) fit = 2;
     // Balanced chunks (not "full, full, ..., sliver"): short rows make poor 2-D copies.
@@ -708,14 +885,9 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
             }
         }
     }
-    if (!direct && b->workers == nullptr) {
-        unsigned threads = pb::default_host_workers();
-        if (const char *e = std::getenv("PERTURB_GPU_HOST_THREADS")) {
-            const int v = std::atoi(e);
-            if (v >= 1 && v <= 256) threads = static_cast<unsigned>(v);
-        }
-        b->workers = new (std::nothrow) pb::HostWorkers(threads);
-        if (b->workers == nullptr) return fail(PERTURB_GPU_ERR_ALLOC, "host allocation failed");
+    if (!direct) {
+        const int st = ensure_workers(b);
+        if (st != PERTURB_GPU_OK) return st;
     }
 
     // Bounce chunk -> the caller's arrays (rows of one chunk, host threads).
@@ -741,7 +913,7 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
                         for (size_t k = 0; k < mk; ++k) clean = clean && (ei[k] == 0 || ei[k] == 6);
                     }
                     if (clean) {
-                        std::memcpy(di, si, mk * 64);
+                        copy_streaming(di, si, mk * 64);
                     } else {
                         for (size_t k = 0; k < mk; ++k) {  // epoch always, r / v for codes 0 and 6
                             const bool written = (ei[k] == 0 || ei[k] == 6);
@@ -750,11 +922,12 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
                     }
                 } else {
                     for (size_t pl = 0; pl < 6; ++pl) {
-                        std::memcpy(posvel + pl * plane_stride + i * row_stride + k0,
-                                    src + (pl * n * ld + i * ld) * sizeof(double), mk * sizeof(double));
+                        copy_streaming(posvel + pl * plane_stride + i * row_stride + k0,
+                                       src + (pl * n * ld + i * ld) * sizeof(double), mk * sizeof(double));
                     }
                 }
             }
+            streaming_fence();
         });
     };
 
@@ -1291,6 +1464,24 @@ int perturb_gpu_host_alloc(size_t bytes, void **out) {
         return fail(PERTURB_GPU_ERR_ALLOC, "cudaHostAlloc failed");
     }
     return PERTURB_GPU_OK;
+}
+
+int perturb_gpu_host_register(void *p, size_t bytes) {
+    if (p == nullptr || bytes == 0) return fail(PERTURB_GPU_ERR_ARG, "null pointer or empty range");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return PERTURB_GPU_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PERTURB_GPU_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    return PERTURB_GPU_OK;
+}
+
+void perturb_gpu_host_unregister(void *p) {
+    if (p != nullptr && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
 }
 
 void perturb_gpu_host_free(void *p) {

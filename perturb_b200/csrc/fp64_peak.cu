@@ -4,6 +4,7 @@
 // run, under the same clocks, and quotes fractions of it next to the nominal
 // 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s.
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include "../../include/perturb_gpu.h"
 #include "../../include/perturb_benchtools.h"
@@ -115,4 +116,65 @@ extern "C" int perturb_gpu_measure_d2h(int device, size_t bytes, int reps, doubl
         *gbs_mean = total_ms > 0.0 ? static_cast<double>(bytes) * reps / (total_ms * 1e-3) * 1e-9 : 0.0;
     }
     return PERTURB_GPU_OK;
+}
+
+// The same from ONE process over several devices at once: every device copies `bytes` bytes
+// `reps` times into its own pinned buffer (allocated with `host_flags`: 0 default,
+// 1 cudaHostAllocPortable, 4 cudaHostAllocWriteCombined, or their sum), all copies in flight
+// together; *gbs_total = all bytes / wall time between the first enqueue and the last
+// completion. With the per-process figure of perturb_gpu_measure_d2h this separates what the
+// box can land in host memory from how the buffers were allocated.
+extern "C" int perturb_gpu_measure_d2h_multi(int n_devices, size_t bytes, int reps,
+                                             unsigned host_flags, double *gbs_total) {
+    if (gbs_total == nullptr || bytes == 0 || reps < 1 || n_devices < 1 || n_devices > 64) {
+        return PERTURB_GPU_ERR_ARG;
+    }
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < n_devices) return PERTURB_GPU_ERR_NODEV;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    void *d[64] = {nullptr}, *h[64] = {nullptr};
+    cudaStream_t st[64] = {nullptr};
+    int status = PERTURB_GPU_OK;
+    for (int g = 0; g < n_devices && status == PERTURB_GPU_OK; ++g) {
+        if (cudaSetDevice(g) != cudaSuccess || cudaMalloc(&d[g], bytes) != cudaSuccess ||
+            cudaHostAlloc(&h[g], bytes, host_flags) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking) != cudaSuccess) {
+            status = PERTURB_GPU_ERR_ALLOC;
+            break;
+        }
+        cudaMemsetAsync(d[g], 1, bytes, st[g]);
+        cudaMemcpyAsync(h[g], d[g], bytes, cudaMemcpyDeviceToHost, st[g]);  // warm-up / first touch
+    }
+    if (status == PERTURB_GPU_OK) {
+        for (int g = 0; g < n_devices; ++g) {
+            cudaSetDevice(g);
+            cudaStreamSynchronize(st[g]);
+        }
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int r = 0; r < reps; ++r) {
+            for (int g = 0; g < n_devices; ++g) {
+                cudaSetDevice(g);
+                cudaMemcpyAsync(h[g], d[g], bytes, cudaMemcpyDeviceToHost, st[g]);
+            }
+        }
+        for (int g = 0; g < n_devices; ++g) {
+            cudaSetDevice(g);
+            cudaStreamSynchronize(st[g]);
+        }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+        *gbs_total = static_cast<double>(bytes) * reps * n_devices / secs * 1e-9;
+        if (cudaGetLastError() != cudaSuccess) status = PERTURB_GPU_ERR_CUDA;
+    }
+    for (int g = 0; g < n_devices; ++g) {
+        cudaSetDevice(g);
+        if (st[g]) cudaStreamDestroy(st[g]);
+        if (h[g]) cudaFreeHost(h[g]);
+        if (d[g]) cudaFree(d[g]);
+    }
+    cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    return status;
 }

@@ -233,7 +233,7 @@ __device__ __forceinline__ void kepler_newton(double u, double axnl, double aynl
         done = done || stop;
         if (!done) eo1 = eo1 + tem5;
         ++ktr;
-    } while (ktr <= 10 && !(UNIFORM ? __all_sync(0xffffffffu, done) : done));
+    } while (ktr <= 10 && !(UNIFORM ? warp_all(done) : done));
     // sin/cos at E + d for the lanes that owe the confirming pass (identity otherwise)
     const double dfin = (done && mag >= kMc[MC_1EM12]) ? tem5 : 0.0;
     const double h = dfin * dfin;
@@ -620,7 +620,7 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     if (UNIFORM && PB_KEPLER_SMALL) {
         const bool small = el2 < kMc[MC_KEPLER_SMALL];
         // ONE vote: both branch decisions below derive from the same warp-uniform mask
-        const unsigned small_lanes = __ballot_sync(0xffffffffu, small);
+        const unsigned small_lanes = warp_ballot(small);
         if (small_lanes == 0xffffffffu) {
             kepler_small(u, axnl, aynl, sineo1, coseo1);
         } else {

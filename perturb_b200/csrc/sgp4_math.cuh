@@ -101,6 +101,40 @@ static __constant__ double kMc[MC_COUNT] = {
     4.0e-4, 1.66666666666666674068e+00,
 };
 
+// ---- warp votes ---------------------------------------------------------------------------
+// Votes of the FULL warp as volatile inline PTX. Kernel 2 keeps its control flow warp-uniform
+// with them (Kepler path choice, Newton loop exit, "every lane has a state to store"). The
+// plain intrinsics are pure functions to the optimiser: in one instantiation (mean-element
+// output, satellites split over the CTA's warps) it sank `__all_sync` below an `if (time index
+// < m)` whose body was its only user, so the lanes past the end of the grid never reached the
+// vote and the warp dead-locked. A volatile asm statement executes exactly where it is written.
+__device__ __forceinline__ unsigned warp_ballot(bool p) {
+    unsigned r;
+    asm volatile(
+        "{ .reg .pred q; setp.ne.u32 q, %1, 0; vote.sync.ballot.b32 %0, q, 0xffffffff; }"
+        : "=r"(r)
+        : "r"(static_cast<unsigned>(p)));
+    return r;
+}
+__device__ __forceinline__ bool warp_all(bool p) { return warp_ballot(p) == 0xffffffffu; }
+// Full-warp integer reductions (redux.sync), volatile for the same reason: their results feed
+// stores that only lane 0 performs.
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned warp_max_u32(unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ int warp_add_s32(int v) {
+    int r;
+    asm volatile("redux.sync.add.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 // ---- reciprocal, division, square root ---------------------------------------------------
 // MUFU.RCP64H / MUFU.RSQ64H seeds (about 20 good bits) refined in FP64. Inputs on
 // this path are normal, finite doubles; zero / infinity / NaN propagate as NaN or infinity

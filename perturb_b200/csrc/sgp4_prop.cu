@@ -249,14 +249,13 @@ constexpr int kModeProximity = 5;   // fused consumer: closest approach to a few
 // Warp-wide minimum of non-negative doubles (they order like their bit patterns) with ties
 // going to the lowest index: three 32-bit reductions. Lanes without a candidate pass +inf, -1.
 __device__ __forceinline__ void warp_min_with_index(double &v, int &k) {
-    const unsigned full = 0xffffffffu;
     const unsigned hi = static_cast<unsigned>(__double2hiint(v));
     const unsigned lo = static_cast<unsigned>(__double2loint(v));
-    const unsigned m_hi = __reduce_min_sync(full, hi);
+    const unsigned m_hi = warp_min_u32(hi);
     bool cand = hi == m_hi;
-    const unsigned m_lo = __reduce_min_sync(full, cand ? lo : 0xffffffffu);
+    const unsigned m_lo = warp_min_u32(cand ? lo : 0xffffffffu);
     cand = cand && lo == m_lo;
-    const unsigned m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(k) : 0xffffffffu);
+    const unsigned m_k = warp_min_u32(cand ? static_cast<unsigned>(k) : 0xffffffffu);
     v = __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo));
     k = static_cast<int>(m_k);
 }
@@ -411,7 +410,7 @@ sgp4_prop_kernel(const PropParams p) {
             }
             const int kt = k_base + i0;
             const bool w0 = (cd[0] == 0) || (cd[0] == 6), w1 = (cd[1] == 0) || (cd[1] == 6);
-            if (!__all_sync(0xffffffffu, w0 && w1)) {
+            if (!warp_all(w0 && w1)) {
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
                     r[0][c] = w0 ? r[0][c] : nan;
@@ -452,7 +451,7 @@ sgp4_prop_kernel(const PropParams p) {
             const int kt = k_base + i0 + kTimeStep * j;
             // every lane of the warp is here (uniform control flow): one vote decides whether
             // the stores need the NaN selects at all
-            const bool all_written = __all_sync(0xffffffffu, (cd == 0) || (cd == 6));
+            const bool all_written = warp_all((cd == 0) || (cd == 6));
             if (WANT_ELEMENTS && kt < p.m) {
                 // what sgp4() leaves in satrec (src/sgp4.cpp:1895-1901); not reached for codes 1, 2
                 const bool stored = side.stage >= 1;
@@ -480,7 +479,7 @@ sgp4_prop_kernel(const PropParams p) {
                     // sin(elevation) = up / range against the mask, without the division
                     const double sin_el = up * rsqrt_fast(range2);
                     const bool visible = ok && sin_el >= q[6];
-                    const unsigned bits = __ballot_sync(0xffffffffu, visible);
+                    const unsigned bits = warp_ballot(visible);
                     // largest sin(elevation) of the 32 times: 1 - sin is non-negative
                     const double gap = 1.0 - sin_el;  // (rounding can leave sin_el a hair above 1)
                     double key = ok ? (gap > 0.0 ? gap : 0.0) : __longlong_as_double(0x7ff0000000000000LL);
@@ -501,7 +500,7 @@ sgp4_prop_kernel(const PropParams p) {
                     const double dx = r[0] - q[0], dy = r[1] - q[p.m], dz = r[2] - q[2 * static_cast<size_t>(p.m)];
                     const double d2v = __fma_rn(dz, dz, mad2(dx, dx, dy, dy));
                     const bool have = ok && (d2v == d2v);  // a primary without a state is skipped
-                    const unsigned below = __ballot_sync(0xffffffffu, have && d2v < p.thr2);
+                    const unsigned below = warp_ballot(have && d2v < p.thr2);
                     double key = have ? d2v : __longlong_as_double(0x7ff0000000000000LL);
                     int kbest = have ? kt : -1;
                     warp_min_with_index(key, kbest);
@@ -566,36 +565,35 @@ sgp4_prop_kernel(const PropParams p) {
             // word, low word among the lanes that match, index among those that match both)
             // instead of five rounds of seven shuffles and a full merge.
             {
-                const unsigned full = 0xffffffffu;
                 // minimum radius: lanes without an ok evaluation hold +inf and index -1
                 unsigned hi = static_cast<unsigned>(__double2hiint(acc.r_min));
                 unsigned lo = static_cast<unsigned>(__double2loint(acc.r_min));
-                unsigned m_hi = __reduce_min_sync(full, hi);
+                unsigned m_hi = warp_min_u32(hi);
                 bool cand = hi == m_hi;
-                unsigned m_lo = __reduce_min_sync(full, cand ? lo : 0xffffffffu);
+                unsigned m_lo = warp_min_u32(cand ? lo : 0xffffffffu);
                 cand = cand && lo == m_lo;
-                unsigned m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(acc.k_min) : 0xffffffffu);
+                unsigned m_k = warp_min_u32(cand ? static_cast<unsigned>(acc.k_min) : 0xffffffffu);
                 acc.r_min = __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo));
                 acc.k_min = static_cast<int>(m_k);
                 // maximum radius: lanes without an ok evaluation (-inf, index -1) count as key 0
                 const bool have = acc.k_max >= 0;
                 hi = have ? static_cast<unsigned>(__double2hiint(acc.r_max)) : 0u;
                 lo = have ? static_cast<unsigned>(__double2loint(acc.r_max)) : 0u;
-                m_hi = __reduce_max_sync(full, hi);
+                m_hi = warp_max_u32(hi);
                 cand = hi == m_hi;
-                m_lo = __reduce_max_sync(full, cand ? lo : 0u);
+                m_lo = warp_max_u32(cand ? lo : 0u);
                 cand = cand && lo == m_lo;
-                m_k = __reduce_min_sync(full, cand ? static_cast<unsigned>(acc.k_max) : 0xffffffffu);
+                m_k = warp_min_u32(cand ? static_cast<unsigned>(acc.k_max) : 0xffffffffu);
                 acc.k_max = static_cast<int>(m_k);
                 acc.r_max = (acc.k_max >= 0)
                                 ? __hiloint2double(static_cast<int>(m_hi), static_cast<int>(m_lo))
                                 : __longlong_as_double(0xfff0000000000000LL);
-                acc.n_ok = __reduce_add_sync(full, acc.n_ok);
+                acc.n_ok = warp_add_s32(acc.n_ok);
                 // first error in time: every lane's index is distinct, so one lane matches
                 const unsigned ke = static_cast<unsigned>(acc.k_err);  // -1 -> 0xffffffff
-                const unsigned m_e = __reduce_min_sync(full, ke);
-                const unsigned code = __reduce_max_sync(
-                    full, (ke == m_e && acc.k_err >= 0) ? static_cast<unsigned>(acc.code_err) : 0u);
+                const unsigned m_e = warp_min_u32(ke);
+                const unsigned code = warp_max_u32(
+                    (ke == m_e && acc.k_err >= 0) ? static_cast<unsigned>(acc.code_err) : 0u);
                 acc.k_err = static_cast<int>(m_e);
                 acc.code_err = static_cast<int>(code);
             }
@@ -634,7 +632,7 @@ sgp4_prop_short_kernel(const PropParams p, int tile_count) {
     constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (__all_sync(0xffffffffu, tile >= tile_count)) return;
+    if (warp_all(tile >= tile_count)) return;
     const size_t slot_own = static_cast<size_t>(p.tile_begin + tile) * PB_TILE_SATS + lane;
     const int dst = p.perm[slot_own];
     // a padding lane (only at the end of a class segment, never first in its tile) redoes the

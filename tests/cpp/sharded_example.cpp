@@ -4,6 +4,7 @@
 // Shards go to distinct devices when the box has several, else all to device 0.
 #include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include <perturb/satellite_batch.hpp>
@@ -111,6 +112,42 @@ int main(int argc, char **argv) {
     std::printf("records_equal %d record_codes_equal %d status %d\n",
                 std::memcmp(sa, sb, plane * 64) == 0,
                 std::memcmp(ca.data(), cb.data(), plane * 4) == 0, sharded.status());
+    // the drop-in calls on the sharded class: ordinary vectors, untouched on errors 1-4, every
+    // shard on its own host thread -- and the from_tles route (text parsed on each shard's device)
+    {
+        std::vector<JulianDate> times(m);
+        for (std::size_t k = 0; k < m; ++k) times[k] = JulianDate(jd[k], fr[k]);
+        StateVector mark = StateVector();
+        mark.position = {{-1.0, -2.0, -3.0}};
+        mark.velocity = {{-4.0, -5.0, -6.0}};
+        std::vector<StateVector> va(plane, mark), vb(plane, mark);
+        std::vector<Sgp4Error> xa(plane), xb(plane);
+        whole.propagate(times.data(), m, va.data(), xa.data());
+        std::vector<std::string> s1(n), s2(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            s1[i].assign(&l1[i * PERTURB_SYNTH_LINE_STRIDE], 69);
+            s2[i].assign(&l2[i * PERTURB_SYNTH_LINE_STRIDE], 69);
+        }
+        ShardedSatelliteBatch from_text = ShardedSatelliteBatch::from_tles(
+            s1.data(), s2.data(), n, devices.data(), n_shards);
+        const int st = from_text.ok() ? from_text.propagate(times.data(), m, vb.data(), xb.data()) : -98;
+        std::size_t untouched = 0;
+        for (std::size_t e = 0; e < plane; ++e) {
+            const int c = static_cast<int>(xa[e]);
+            if (c >= 1 && c <= 4) {
+                untouched += std::memcmp(&va[e].position, &mark.position, 48) == 0;
+            }
+        }
+        std::size_t failed = 0;
+        for (std::size_t e = 0; e < plane; ++e) {
+            const int c = static_cast<int>(xa[e]);
+            failed += (c >= 1 && c <= 4);
+        }
+        std::printf("dropin_equal %d dropin_codes_equal %d status %d failed %zu untouched %zu cuts_equal %d\n",
+                    std::memcmp(va.data(), vb.data(), plane * 64) == 0,
+                    std::memcmp(xa.data(), xb.data(), plane * 4) == 0, st, failed, untouched,
+                    from_text.shard_end(0) == sharded.shard_end(0));
+    }
     ShardedSatelliteBatch::pinned_free(pa);
     ShardedSatelliteBatch::pinned_free(pb);
     ShardedSatelliteBatch::pinned_free(ea);

@@ -4,7 +4,8 @@
 // SURVEY.md 8f N2) and compares `sat_rec` member by member with what the reference itself holds
 // after the same call sequence:
 //   * integer / character members and `t`, `atime`: bit for bit;
-//   * double members: relative difference reported (device math is not glibc's).
+//   * double members: difference reported as a fraction of rel * |x| + abs (device math is not
+//     glibc's): 1e-11 / 1e-14 for the initialised record, 1e-9 / 1e-10 for the per-call members.
 // Compiled here against /root/reference/include by __graft_entry__.build() (the GPU box has no
 // reference tree: the binary travels); run by tests/test_cpp_api.py under -m gpu.
 //
@@ -40,17 +41,18 @@ static bool compared(const char *name) {
     return true;
 }
 
-// Difference of one double member: `t` and `atime` must be the reference's bits (they are sums
-// of exactly representable terms); angles are compared absolutely (a mean anomaly near zero has
-// no meaningful relative error); everything else relatively.
+// Difference of one double member as a fraction of its allowance (> 1 fails): `t` and `atime`
+// must be the reference's bits (sums of exactly representable terms); everything else may differ
+// by rel * |x| + abs -- kernel 1 rounds like the reference apart from libdevice vs glibc (a few
+// 1e-14, amplified by 1 - cos^2 style cancellations near i = 0: hence the absolute floor, the same
+// allowance as tests/test_gpu_parity.py::test_verification_catalogue_init); the per-call members
+// come from kernel 2's fused arithmetic and carry the states' parity bar instead.
+static double g_rel = 1e-11, g_abs = 1e-14;
+
 static double metric(const char *name, double x, double y) {
-    if (!std::strcmp(name, "t") || !std::strcmp(name, "atime")) return 1.0;
-    if (!(x == x) || !(y == y)) return (x != x && y != y) ? 0.0 : 1.0;
-    static const char *angles[] = {"Om", "om", "mm", "im", "xli", "xlamo", "gsto", "zmol", "zmos"};
-    for (const char *a : angles) {
-        if (!std::strcmp(a, name)) return std::fabs(x - y);
-    }
-    return std::fabs(x - y) / std::fmax(std::fabs(x), 1e-300);
+    if (!std::strcmp(name, "t") || !std::strcmp(name, "atime")) return 2.0;
+    if (!(x == x) || !(y == y)) return (x != x && y != y) ? 0.0 : 2.0;
+    return std::fabs(x - y) / (g_rel * std::fabs(x) + g_abs);
 }
 
 static void compare(const std::vector<Satellite> &want, const std::vector<Satellite> &got,
@@ -140,6 +142,8 @@ int main(int argc, char **argv) {
     compare(sats, copy, valid, w_init);
 
     // (2) the per-call side effects, after the same call sequence
+    g_rel = 1e-9;   // 1e-6 km over 1e3 km: the states' bar, relative
+    g_abs = 1e-10;  // angles [rad], Earth radii
     Worst w_call;
     const double days[] = {0.0, 0.25, 0.5, 3.3, 6.9, -0.35, 1.0};
     std::size_t code_mismatch = 0, calls = 0;
@@ -162,9 +166,9 @@ int main(int argc, char **argv) {
     std::printf(
         "{\"satellites\": %zu, \"init_error_mismatch\": %zu, "
         "\"export\": {\"int_char_mismatch\": %zu, \"doubles\": %zu, \"bit_equal\": %zu, "
-        "\"worst_rel\": %.3g, \"worst_member\": \"%s\", \"worst_sat\": %zu}, "
+        "\"worst_ratio\": %.3g, \"worst_member\": \"%s\", \"worst_sat\": %zu}, "
         "\"write_back\": {\"calls\": %zu, \"code_mismatch\": %zu, \"int_char_mismatch\": %zu, "
-        "\"doubles\": %zu, \"bit_equal\": %zu, \"worst_rel\": %.3g, \"worst_member\": \"%s\", "
+        "\"doubles\": %zu, \"bit_equal\": %zu, \"worst_ratio\": %.3g, \"worst_member\": \"%s\", "
         "\"worst_sat\": %zu}}\n",
         n, init_mismatch, w_init.int_mismatch, w_init.doubles, w_init.exact, w_init.rel,
         w_init.member.c_str(), w_init.sat, calls, code_mismatch, w_call.int_mismatch, w_call.doubles,

@@ -138,6 +138,11 @@ def test_cpp_sharded_batch_equals_the_unsharded_one(tmp_path, shards):
     assert "planes_equal 1 codes_equal 1" in out, out
     assert "records_equal 1 record_codes_equal 1 status 0" in out, out
     assert "device_gather_equal 1 device_gather_codes_equal 1 status 0" in out, out
+    # ShardedSatelliteBatch::from_tles + propagate(JulianDate*, m, StateVector*, Sgp4Error*): the
+    # unsharded drop-in's bits, failed evaluations left untouched, same range plan
+    drop = [ln for ln in out.splitlines() if ln.startswith("dropin_equal")][0].split()
+    assert drop[1] == "1" and drop[3] == "1" and drop[5] == "0", out
+    assert drop[7] == drop[9] and drop[11] == "1", out
     cuts = [int(x) for x in out.splitlines()[0].split("cuts")[1].split()]
     assert len(cuts) == shards and cuts[-1] == 3000
 

@@ -107,6 +107,18 @@ def test_propagate_into_leaves_failed_states_untouched(ops):
     assert np.array_equal(_bits(states["velocity"][ok]), _bits(nan_rec["velocity"][ok]))
     assert np.array_equal(_bits(states["epoch_jd"]), _bits(nan_rec["epoch_jd"]))
     assert np.array_equal(_bits(states["epoch_jd_frac"]), _bits(nan_rec["epoch_jd_frac"]))
+    # the same into memory the caller page-locked in place: direct DMA + save / restore
+    pinned = np.zeros_like(states)
+    pinned["position"] = -1.0
+    pinned["velocity"] = -2.0
+    perr = np.full_like(err, -9)
+    capi.check(capi.lib().perturb_gpu_host_register(pinned.ctypes.data, pinned.nbytes), "host_register")
+    try:
+        batch.propagate_into(mins, None, pinned, perr)
+    finally:
+        capi.lib().perturb_gpu_host_unregister(pinned.ctypes.data)
+    assert np.array_equal(perr, err)
+    assert np.array_equal(pinned.view(np.int64), states.view(np.int64))
     # err may be omitted, like a caller who ignores the return value
     again = np.zeros_like(states)
     again["position"] = -1.0
@@ -192,16 +204,17 @@ def test_write_back_matches_the_reference_records():
         pytest.skip("writeback_check was not built (needs the reference tree at build time)")
     for cfg, n in ((3, 3000), (4, 1000)):
         out = subprocess.run([exe, str(cfg), str(n)], capture_output=True, text=True, timeout=600)
+        print(out.stdout, out.stderr[-3000:])
         assert out.returncode == 0, out.stdout + out.stderr[-2000:]
         r = json.loads(out.stdout.strip().splitlines()[-1])
         print(json.dumps(r))
         assert r["init_error_mismatch"] == 0
         assert r["export"]["int_char_mismatch"] == 0 and r["write_back"]["int_char_mismatch"] == 0
         assert r["write_back"]["code_mismatch"] == 0
-        # kernel 1 rounds like the reference except for libdevice vs glibc: a few 1e-14
-        assert r["export"]["worst_rel"] < 1e-9, r["export"]
-        # per-call members: mean elements to the parity bar of the states (1e-6 km / 42 000 km)
-        assert r["write_back"]["worst_rel"] < 1e-9, r["write_back"]
+        # worst difference as a fraction of the allowance (1e-11 |x| + 1e-14 for the initialised
+        # record, 1e-9 |x| + 1e-10 for the per-call members; t and atime bit for bit)
+        assert r["export"]["worst_ratio"] < 1.0, r["export"]
+        assert r["write_back"]["worst_ratio"] < 1.0, r["write_back"]
 
 
 def test_argument_validation_of_the_python_mirror():
