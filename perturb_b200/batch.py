@@ -118,6 +118,8 @@ def _check_output(x, what, dtype, shape_min, last_contiguous=True):
     shape = tuple(x.shape)
     if len(shape) != len(shape_min) or any(a < b for a, b in zip(shape, shape_min)):
         raise ValueError("%s has shape %s, need at least %s" % (what, shape, tuple(shape_min)))
+    if 0 in shape:
+        return  # nothing will be written; the strides of an empty array mean nothing
     if last_contiguous and shape[-1] > 1 and _elem_strides(x)[-1] != 1:
         raise ValueError("%s: the last axis must be contiguous" % what)
 

@@ -25,11 +25,11 @@
 using namespace perturb;
 
 struct Worst {
-    double rel;
+    double rel, want, got;
     std::string member;
     std::size_t sat;
     std::size_t exact, doubles, int_mismatch;
-    Worst() : rel(0.0), sat(0), exact(0), doubles(0), int_mismatch(0) {}
+    Worst() : rel(0.0), want(0.0), got(0.0), sat(0), exact(0), doubles(0), int_mismatch(0) {}
 };
 
 // members the reference never sets from a TLE or leaves to the caller are not compared
@@ -75,6 +75,8 @@ static void compare(const std::vector<Satellite> &want, const std::vector<Satell
                 if (d > w.rel) {                                                                \
                     w.rel = d;                                                                  \
                     w.member = #name;                                                           \
+                    w.want = x;                                                                 \
+                    w.got = y;                                                                  \
                     w.sat = i;                                                                  \
                 }                                                                               \
             }                                                                                   \
@@ -166,12 +168,12 @@ int main(int argc, char **argv) {
     std::printf(
         "{\"satellites\": %zu, \"init_error_mismatch\": %zu, "
         "\"export\": {\"int_char_mismatch\": %zu, \"doubles\": %zu, \"bit_equal\": %zu, "
-        "\"worst_ratio\": %.3g, \"worst_member\": \"%s\", \"worst_sat\": %zu}, "
+        "\"worst_ratio\": %.3g, \"worst_member\": \"%s\", \"worst_sat\": %zu, \"want\": %.17g, \"got\": %.17g}, "
         "\"write_back\": {\"calls\": %zu, \"code_mismatch\": %zu, \"int_char_mismatch\": %zu, "
         "\"doubles\": %zu, \"bit_equal\": %zu, \"worst_ratio\": %.3g, \"worst_member\": \"%s\", "
         "\"worst_sat\": %zu}}\n",
         n, init_mismatch, w_init.int_mismatch, w_init.doubles, w_init.exact, w_init.rel,
-        w_init.member.c_str(), w_init.sat, calls, code_mismatch, w_call.int_mismatch, w_call.doubles,
+        w_init.member.c_str(), w_init.sat, w_init.want, w_init.got, calls, code_mismatch, w_call.int_mismatch, w_call.doubles,
         w_call.exact, w_call.rel, w_call.member.c_str(), w_call.sat
     );
     return 0;
