@@ -450,6 +450,93 @@ def dropin_harness(workload, local, steps):
     return rec
 
 
+def e2e_host_planes(pb, torch, batch, n, m, world, local, dev, dist, steps, bind=True):
+    """The hot path through the C ABI with HOST buffers: H2D of the time grid, kernel 2, D2H of
+    all states and codes into pinned memory inside the timed region (wall clock, max over ranks).
+    Returns the record and the pinned grid / code buffers for the next arm."""
+    numa = bind_to_gpu_numa_node(local) if bind else "numa: binding off"
+    me = min(m, E2E_MAX_TIMES)
+    jd, fr = pb.synth_time_grid(m)
+    h_jd = torch.tensor(jd[:me]).pin_memory()
+    h_fr = torch.tensor(fr[:me]).pin_memory()
+    h_out = torch.empty((6, n, me), dtype=torch.float64).pin_memory()
+    h_err = torch.empty((n, me), dtype=torch.int32).pin_memory()
+    batch.propagate(h_jd, h_fr, h_out, h_err)  # warm-up: allocates the staging buffers
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    te = time.perf_counter()
+    for _ in range(steps):
+        batch.propagate(h_jd, h_fr, h_out, h_err)  # synchronises: results are on the host
+        _ = int(h_err[0, 0])
+    own_s = time.perf_counter() - te
+    e2e_s = pb.max_over_ranks(own_s, dist, dev)
+    rec = {
+        "value": float(n) * me * world * steps / e2e_s,
+        "unit": "evals/s",
+        "h2d_bytes_per_step": int(2 * me * 8),
+        "d2h_bytes_per_step": int(float(n) * me * 52),
+        "times_per_step": me,
+        "steps": steps,
+        "host_buffers": "pinned",
+        "placement": numa,
+        "d2h_gbs": float(n) * me * world * steps * BYTES_PER_EVAL / e2e_s * 1e-9,
+        "d2h_gbs_this_rank": float(n) * me * steps * BYTES_PER_EVAL / own_s * 1e-9,
+        "ok_fraction": float((h_err == 0).double().mean()),
+    }
+    del h_out
+    return rec, h_jd, h_fr, h_err
+
+
+def d2h_ceiling(pb, torch, world, local, dev, dist, window_s=1.0):
+    """Raw D2H ceiling of the box: after a barrier every rank copies 256 MiB pieces device ->
+    pinned host back to back for the same `window_s` seconds; a rank's rate is the bytes it
+    landed in that window, the aggregate is the sum over ranks -- what N GPUs can put into host
+    memory when all of them copy all the time. (Summing rates that each rank measured over its
+    own copies overstates it: the ranks' copies need not overlap.) Equal satellite shards finish
+    with the slowest GPU, so the bound for the e2e arm is N x the slowest rank's rate."""
+    piece = 256 << 20
+    d = torch.empty(piece, dtype=torch.uint8, device=dev)
+    d.fill_(1)
+    h = torch.empty(piece, dtype=torch.uint8).pin_memory()
+    h.copy_(d, non_blocking=True)  # first touch, untimed
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        now = time.perf_counter() - t0
+        if now > window_s:
+            break
+        done += piece
+    own = done / window_s * 1e-9
+    slowest = -pb.max_over_ranks(-own, dist, dev)
+    total = own
+    if dist is not None:
+        t = torch.tensor([own], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        total = float(t.item())
+    del d, h
+    return {"d2h_ceiling_gbs": total,
+            "d2h_ceiling_gbs_slowest_gpu": slowest,
+            "d2h_ceiling_gbs_equal_shards": slowest * world,
+            "d2h_ceiling_how": "all %d ranks at once, after a barrier: 256 MiB cudaMemcpyAsync pieces "
+                               "device -> pinned host back to back for %.1f s each; bytes landed in the "
+                               "common window, summed over ranks; equal_shards = N x the slowest rank "
+                               "(equal satellite shards finish with the slowest GPU)" % (world, window_s)}
+
+
+def add_ceiling_fractions(e2e):
+    if e2e.get("d2h_ceiling_gbs_equal_shards"):
+        e2e["frac_of_ceiling"] = e2e["d2h_gbs"] / e2e["d2h_ceiling_gbs_equal_shards"]
+    if e2e.get("d2h_ceiling_gbs"):
+        e2e["frac_of_aggregate_ceiling"] = e2e["d2h_gbs"] / e2e["d2h_ceiling_gbs"]
+
+
 def run_gpu(args):
     import torch
     import perturb_b200 as pb
@@ -508,28 +595,30 @@ def run_gpu(args):
 
     # ---- end to end through the C ABI with HOST buffers ----
     all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa_node(local)
     me = min(m, E2E_MAX_TIMES)
     jd, fr = pb.synth_time_grid(m)
-    h_jd = torch.tensor(jd[:me]).pin_memory()
-    h_fr = torch.tensor(fr[:me]).pin_memory()
-    h_out = torch.empty((6, n, me), dtype=torch.float64).pin_memory()
-    h_err = torch.empty((n, me), dtype=torch.int32).pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
-    batch.propagate(h_jd, h_fr, h_out, h_err)  # warm-up: allocates the staging buffers
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
-        batch.propagate(h_jd, h_fr, h_out, h_err)  # synchronises: results are on the host
-        _ = int(h_err[0, 0])
-    e2e_s = pb.max_over_ranks(time.perf_counter() - te, dist, dev)
-    e2e_value = float(n) * me * world * e2e_steps / e2e_s
-    e2e_gbs = float(n) * me * world * e2e_steps * BYTES_PER_EVAL / e2e_s * 1e-9
-    codes_ok = float((h_err == 0).double().mean())
+    e2e, h_jd, h_fr, h_err = e2e_host_planes(pb, torch, batch, n, m, world, local, dev, dist,
+                                             e2e_steps, bind=os.environ.get("PERTURB_BENCH_NUMA", "on") != "off")
+    codes_ok = e2e.pop("ok_fraction")
+    if args.e2e_only:
+        e2e.update(d2h_ceiling(pb, torch, world, local, dev, dist))
+        add_ceiling_fractions(e2e)
+        per_rank = [None] * world
+        if dist is not None:
+            dist.all_gather_object(per_rank, e2e["d2h_gbs_this_rank"])
+        else:
+            per_rank = [e2e["d2h_gbs_this_rank"]]
+        if rank == 0:
+            print(json.dumps({"e2e_only": True, "n_gpus": world, "workload": args.workload,
+                              "host_chunks": os.environ.get("PERTURB_GPU_HOST_CHUNKS"),
+                              "value_device_resident": value, "e2e": e2e,
+                              "d2h_gbs_per_rank": per_rank}))
+        batch.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     # ---- the same through perturb_gpu_propagate_states: the caller's StateVector[n * m] ----
-    del h_out
     h_states = torch.empty((n, me, 8), dtype=torch.float64).pin_memory()
     batch.propagate_states(h_jd, h_fr, h_states, h_err)  # warm-up (staging buffers)
     if dist is not None:
@@ -542,29 +631,7 @@ def run_gpu(args):
     rec_s = pb.max_over_ranks(time.perf_counter() - tr, dist, dev)
     rec_value = float(n) * me * world * e2e_steps / rec_s
     del h_states, h_err
-    # ---- raw D2H ceiling of the box: every rank copies device -> pinned host at the same time
-    # (one cudaMemcpyAsync per repetition), the aggregate is what N GPUs can land in host memory
-    best, mean = pb.capi.C.c_double(0.0), pb.capi.C.c_double(0.0)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    tc = time.perf_counter()
-    ceiling_bytes, ceiling_reps = 1 << 30, 4
-    st = pb.capi.tools().perturb_gpu_measure_d2h(local, ceiling_bytes, ceiling_reps,
-                                                 pb.capi.C.byref(best), pb.capi.C.byref(mean))
-    ceil_s = pb.max_over_ranks(time.perf_counter() - tc, dist, dev)
-    d2h_mean_min = -pb.max_over_ranks(-mean.value, dist, dev)  # slowest rank's rate
-    d2h_mean_sum = mean.value
-    if dist is not None:
-        t = torch.tensor([mean.value], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
-        d2h_mean_sum = float(t.item())
-    ceiling = {"d2h_ceiling_gbs": d2h_mean_sum if st == 0 else None,
-               "d2h_ceiling_gbs_slowest_gpu": d2h_mean_min if st == 0 else None,
-               "d2h_ceiling_how": "all %d ranks at once: %d x cudaMemcpyAsync of 1 GiB device -> "
-                                  "pinned host each (after one untimed copy), sum of the per-rank "
-                                  "mean rates" % (world, ceiling_reps),
-               "d2h_ceiling_wall_s": ceil_s}
+    ceiling = d2h_ceiling(pb, torch, world, local, dev, dist)
     # ---- the fused consumer (N3): host time grid in, one 40-byte summary per satellite out ----
     hs_jd = torch.tensor(jd).pin_memory()
     hs_fr = torch.tensor(fr).pin_memory()
@@ -702,20 +769,8 @@ def run_gpu(args):
     traffic = prof.get(args.workload)
     pipe = fp64_pipe_share(prof, cls, m, launch_ms, clocks.get("sm_mhz"))
     cpu = cpu_arm(args.workload, 2, 1)
-    e2e = {
-        "value": e2e_value,
-        "unit": "evals/s",
-        "h2d_bytes_per_step": int(2 * me * 8),
-        "d2h_bytes_per_step": int(float(n) * me * 52),
-        "times_per_step": me,
-        "steps": e2e_steps,
-        "host_buffers": "pinned",
-        "placement": numa,
-        "d2h_gbs": e2e_gbs,
-    }
     e2e.update(ceiling)
-    if ceiling["d2h_ceiling_gbs"]:
-        e2e["frac_of_ceiling"] = e2e_gbs / ceiling["d2h_ceiling_gbs"]
+    add_ceiling_fractions(e2e)
     line = {
         "metric": "SGP4 evals/sec (sat x time)",
         "value": value,
@@ -808,6 +863,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--quick", action="store_true",
                     help="device-resident timing only (no e2e, no CPU arm): kernel tuning sweeps")
+    ap.add_argument("--e2e-only", action="store_true",
+                    help="device-resident timing + the pinned-host arm + the D2H ceiling only "
+                         "(multi-GPU host-ingest diagnostics; PERTURB_BENCH_NUMA=off skips the binding)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the other BASELINE configs and the in-process multi-GPU check")
     args = ap.parse_args()

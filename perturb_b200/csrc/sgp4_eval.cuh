@@ -31,6 +31,10 @@
 #define PB_KEPLER_SMALL 1  // 0: every orbit through the Newton iteration (bisecting / comparison builds)
 #endif
 
+#ifndef PB_KEPLER_ROT
+#define PB_KEPLER_ROT 1  // 0: sin/cos of the argument of latitude from its reduced value (comparison builds)
+#endif
+
 namespace pb {
 
 // getgravconst() results the evaluation needs (src/sgp4.cpp:2101-2157), batch-wide.
@@ -256,10 +260,10 @@ __device__ __forceinline__ void kepler_newton(double u, double axnl, double aynl
 // sin/cos, where the Newton iteration from E = u needs two or three. The reference stops once
 // a correction is below 1e-12 without applying it, so its own E sits within 1e-12 of the same
 // root (7e-9 km at LEO): both agree to that, far inside the parity bar.
-__device__ __forceinline__ void kepler_small(double u, double axnl, double aynl, double &sineo1,
-                                             double &coseo1) {
-    double su, cu;
-    sincos_cw(u, su, cu);
+// (su, cu) = (sin u, cos u) come from the caller: the general routine on u, or rotations of
+// sines and cosines the evaluation already holds (sgp4_eval, near-Earth full-drag class).
+__device__ __forceinline__ void kepler_small_sc(double su, double cu, double axnl, double aynl,
+                                                double &sineo1, double &coseo1) {
     const double g0 = msb2(axnl, su, aynl, cu);
     const double g1 = mad2(axnl, cu, aynl, su);
     const double a = __dadd_rn(__fma_rn(__fma_rn(g1, g1, g1), g1, g1), 1.0);  // 1 + g1 + g1^2 + g1^3
@@ -274,6 +278,23 @@ __device__ __forceinline__ void kepler_small(double u, double axnl, double aynl,
     const double c2 = __fma_rn(-sd, step, cd);  // step^2 / 2 < 3e-17
     sineo1 = mad2(su, c2, cu, s2);
     coseo1 = msb2(cu, c2, su, s2);
+}
+__device__ __forceinline__ void kepler_small(double u, double axnl, double aynl, double &sineo1,
+                                             double &coseo1) {
+    double su, cu;
+    sincos_cw(u, su, cu);
+    kepler_small_sc(su, cu, axnl, aynl, sineo1, coseo1);
+}
+
+// sqrt(1 - x) for 0 <= x < 4e-4 (the nearly circular orbits of kepler_small): binomial series
+// through x^4 (next term 7 x^5 / 256 < 3e-19). Every coefficient is an FP64 immediate: four FMAs
+// instead of a reciprocal square root seed with two Newton steps, the square-root step and the
+// x == 0 select.
+__device__ __forceinline__ double sqrt_1m_small(double x) {
+    double p = __fma_rn(-0.0390625, x, -0.0625);
+    p = __fma_rn(p, x, -0.125);
+    p = __fma_rn(p, x, -0.5);
+    return __fma_rn(p, x, 1.0);
 }
 
 // Returns the raw sgp4 error code (0, 1, 2, 3, 4, 6). out[0..2] = r [km], out[3..5] = v
@@ -305,6 +326,12 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const bool deep = T::kStatic ? T::kDeep : rt.deep;
     const bool simp = T::kStatic ? T::kSimp : rt.isimp;
     const int irez = T::kStatic ? T::kIrez : rt.irez;
+    // Near-Earth full-drag orbits (kernel 2, compile-time class): sin/cos of the argument of
+    // latitude come from rotations of sines and cosines this evaluation already holds (see the
+    // Kepler section); rot_* carry sin/cos(xmdf) and the small angles that were added to it.
+    constexpr bool kRotU =
+        UNIFORM && (PB_KEPLER_ROT != 0) && T::kStatic && !T::kDeep && !T::kSimp;
+    double rot_sm = 0.0, rot_cm = 1.0, rot_eps = 0.0;
     if (WANT_SIDE) {
         side->stage = 0;
         side->resonant = false;
@@ -336,6 +363,11 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         const double temp = delomg + delm;
         mm = xmdf + temp;
         argpm = argpdf - temp;
+        if (kRotU) {
+            rot_sm = sinm;
+            rot_cm = cosm;
+            rot_eps = temp;
+        }
         const double t3 = t2 * t;
         const double t4 = t3 * t;
         tempa = tempa - k(PF_D2) * t2 - k(PF_D3) * t3 - k(PF_D4) * t4;
@@ -461,7 +493,14 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     em = em - tempe;
     PB_FAIL_IF(em >= 1.0 || em < -kMc[MC_1EM3], 1);  // :1873
     if (em < kMc[MC_1EM6]) em = kMc[MC_1EM6];
-    mm = mm + no * templ;
+    if (kRotU) {
+        const double nt = __dmul_rn(no, templ);
+        rot_eps = rot_eps + nt;
+        mm = mm + nt;
+    } else {
+        mm = mm + no * templ;
+    }
+    const double mm_raw = mm;  // xmdf + drag corrections, unreduced
     double xlm = mm + argpm + nodem;
 
     if (deep || WANT_SIDE) {
@@ -481,13 +520,13 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
             xlm = wrap_pi(xlm);
             mm = wrap_pi(xlm - argpm - nodem);
         }
-    } else {
+    } else if (!kRotU) {
         // near-Earth: nodem (~0.1 rad a week) and argpm (~0.5 rad a week) likewise stay
         // unreduced; the fast angle, the mean anomaly, is reduced exactly where the reference
         // reduces it (:1884-1887)
         xlm = wrap_pi(xlm);
         mm = wrap_pi(xlm - argpm - nodem);
-    }
+    }  // kRotU: the mean anomaly only enters u, which is formed from mm_raw (Kepler section)
 
     if (WANT_SIDE && code == 0) {
         side->am = am;
@@ -606,9 +645,6 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double axnl = ep * cosargp;
     double temp = rcp_fast(am * (1.0 - ep * ep));
     const double aynl = mad2(ep, sinargp, temp, aycof);
-    const double xl = mp + argpp + nodep + temp * xlcof * axnl;
-
-    const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
     const double el2 = mad2(axnl, axnl, aynl, aynl);
     // Kepler's equation  E = u - aynl cos E + axnl sin E  (src/sgp4.cpp:1965-1983). Nearly
     // circular orbits (el2 < 4e-4, i.e. e < 0.02: most of any catalogue) are solved for
@@ -616,24 +652,63 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     // everything else runs the reference's Newton iteration (kepler_newton). The choice is made
     // per lane from the lane's own el2 -- a result never depends on the other lanes of the warp
     // -- while the branches are taken on warp votes, so control flow stays warp-uniform.
-    double sineo1, coseo1;
-    if (UNIFORM && PB_KEPLER_SMALL) {
-        const bool small = el2 < kMc[MC_KEPLER_SMALL];
-        // ONE vote: both branch decisions below derive from the same warp-uniform mask
+    // betal = sqrt(1 - el2) (:1998) follows the same split: a four-term series where el2 < 4e-4.
+    double sineo1 = 0.0, coseo1 = 1.0, betal = 1.0;
+    if (kRotU) {
+        // u = xl - nodep = mp + argpp + dxl (mod 2 pi) with mp = xmdf + (drag corrections) and
+        // sin/cos of xmdf and of argpp both at hand: (sin u, cos u) is (sin, cos)(xmdf) rotated
+        // by argpp and then by the small angle eps = drag corrections + dxl (a few 1e-3 rad after
+        // a day, ~1e-2 after a week: Taylor sums, truncation < 3e-19 below 2^-4). No range
+        // reduction of xlm, mm and u (the reference's three fmod calls, :1884-1887, 1963) and no
+        // general sin/cos of u: 19 FP64 operations instead of 36, no quadrant logic. A lane whose
+        // eps is larger (strong drag, weeks from epoch) takes the general route with the lanes
+        // that are not nearly circular; u itself is only formed there, as Newton's starting value.
+        const double dxl = temp * xlcof * axnl;
+        const double eps = rot_eps + dxl;
+        const bool small = (el2 < kMc[MC_KEPLER_SMALL]) && (fabs(eps) < 0.0625);
         const unsigned small_lanes = warp_ballot(small);
-        if (small_lanes == 0xffffffffu) {
-            kepler_small(u, axnl, aynl, sineo1, coseo1);
-        } else {
-            kepler_newton<true>(u, axnl, aynl, sineo1, coseo1);
-            if (small_lanes != 0u) {
-                double sf, cf;
-                kepler_small(u, axnl, aynl, sf, cf);
-                sineo1 = small ? sf : sineo1;
-                coseo1 = small ? cf : coseo1;
-            }
+        if (small_lanes != 0u) {
+            double s1, c1, se, ce, su, cu;
+            rotate(rot_sm, rot_cm, sinargp, cosargp, s1, c1);
+            sincos_taylor<4, 4>(eps, se, ce);
+            rotate(s1, c1, se, ce, su, cu);
+            kepler_small_sc(su, cu, axnl, aynl, sineo1, coseo1);
+            betal = sqrt_1m_small(el2);
+        }
+        if (small_lanes != 0xffffffffu) {
+            const double u = wrap_pi((mm_raw + argpp) + dxl);
+            double sn, cn;
+            kepler_newton<true>(u, axnl, aynl, sn, cn);
+            const double bn = sqrt_fast(1.0 - el2);
+            sineo1 = small ? sineo1 : sn;
+            coseo1 = small ? coseo1 : cn;
+            betal = small ? betal : bn;
         }
     } else {
-        kepler_newton<UNIFORM>(u, axnl, aynl, sineo1, coseo1);
+        const double xl = mp + argpp + nodep + temp * xlcof * axnl;
+        const double u = wrap_pi(xl - nodep);  // fmod(xl - nodep, twopi); only u mod 2pi matters
+        if (UNIFORM && PB_KEPLER_SMALL) {
+            const bool small = el2 < kMc[MC_KEPLER_SMALL];
+            // ONE vote: both branch decisions below derive from the same warp-uniform mask
+            const unsigned small_lanes = warp_ballot(small);
+            if (small_lanes == 0xffffffffu) {
+                kepler_small(u, axnl, aynl, sineo1, coseo1);
+                betal = sqrt_1m_small(el2);
+            } else {
+                kepler_newton<true>(u, axnl, aynl, sineo1, coseo1);
+                betal = sqrt_fast(1.0 - el2);
+                if (small_lanes != 0u) {
+                    double sf, cf;
+                    kepler_small(u, axnl, aynl, sf, cf);
+                    sineo1 = small ? sf : sineo1;
+                    coseo1 = small ? cf : coseo1;
+                    betal = small ? sqrt_1m_small(el2) : betal;
+                }
+            }
+        } else {
+            kepler_newton<UNIFORM>(u, axnl, aynl, sineo1, coseo1);
+            betal = sqrt_fast(1.0 - el2);
+        }
     }
 
     // ---- short-period preliminary quantities, src/sgp4.cpp:1986-2011 ----
@@ -645,7 +720,6 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
     const double rl = am * (1.0 - ecose);
     const double inv_rl = rcp_fast(rl);
     const double rdotl = sqrt_am * esine * inv_rl;
-    const double betal = sqrt_fast(1.0 - el2);
     const double rvdotl = (sqrt_am * betal) * inv_rl;  // sqrt(pl) = sqrt(am) sqrt(1 - el2)
     temp = esine * rcp_fast(1.0 + betal);
     const double aorl = am * inv_rl;
@@ -692,20 +766,22 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         // beta = sqrt(1 - e^2), sinu^2 + cosu^2 == 1 is an algebraic identity in E (any E,
         // converged or not), so atan2 followed by sin/cos would only remove rounding noise of
         // a few 1e-16 (times a/r near the perigee of a very eccentric orbit) from the norm.
-        const double su_s = sinu, su_c = cosu;
-        double sd, cd;
-        sincos_small<9>(dsu, sd, cd);
-        sinsu = msb2(su_s, cd, su_c, sd);
-        cossu = mad2(su_c, cd, su_s, sd);
-    }
-    sincos_cw(xnode, snod, cnod);
-    {
-        // xinc = xincp + dxi with dxi ~ 1e-3 and sin/cos(xincp) already at hand
-        double sdx, cdx;
-        sincos_small<9>(dxi, sdx, cdx);
+        // xinc = xincp + dxi likewise, with sin/cos(xincp) already at hand. Both corrections are
+        // ~1e-3 rad for every physical orbit: two-coefficient Taylor sums, and ONE fall-back
+        // region for the garbage states where either is not small (decided per lane).
+        double sd, cd, sdx, cdx;
+        sincos_series<9>(dsu, sd, cd);
+        sincos_series<9>(dxi, sdx, cdx);
+        if (!(fabs(dsu) < 0.001953125 && fabs(dxi) < 0.001953125)) {
+            sincos_cw(dsu, sd, cd);
+            sincos_cw(dxi, sdx, cdx);
+        }
+        sinsu = msb2(sinu, cd, cosu, sd);
+        cossu = mad2(cosu, cd, sinu, sd);
         sini = mad2(sinip, cdx, cosip, sdx);
         cosi = msb2(cosip, cdx, sinip, sdx);
     }
+    sincos_cw(xnode, snod, cnod);
     const double xmx = -snod * cosi;
     const double xmy = cnod * cosi;
     const double ux = mad2(xmx, sinsu, cnod, cossu);

@@ -54,6 +54,9 @@ constexpr int kTimeTile = kThreads * kTpl;     // times per CTA
 #ifndef PB_TPL_PAIR
 #define PB_TPL_PAIR 0
 #endif
+#ifndef PB_SMEM_VECTOR_ADDR
+#define PB_SMEM_VECTOR_ADDR 1
+#endif
 constexpr bool kPair = (PB_TPL_PAIR != 0) && (kTpl == 2);
 
 template <int CLS>
@@ -371,7 +374,9 @@ sgp4_prop_kernel(const PropParams p) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     double gm_s = 0.0, gm_c = 1.0;
     if (MODE == kModeVisibility) {
+#ifndef PB_SWEEP_BUILD  // (kernel sweeps build PB_TPL = 2 libraries to time the states mode only)
         static_assert(MODE != kModeVisibility || kTpl == 1, "fused screens are built for one time per lane");
+#endif
         const int kc = min(k_base + i0, p.m - 1);
         gm_s = p.gmst[2 * kc];
         gm_c = p.gmst[2 * kc + 1];
@@ -381,7 +386,15 @@ sgp4_prop_kernel(const PropParams p) {
     for (int s = SPLIT ? sat_first : 0; s < SATS; s += SPLIT ? sat_step : 1) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
-        const SmemConsts<CLS> k = {s_pf + s * kRowsPad};
+        // The satellite's block is addressed through a VECTOR register (the offset is made opaque
+        // to the uniformity analysis): kept uniform, ptxas re-forms the shared-window address
+        // (S2UR CgaCtaId, UMOV, ULEA, UIMAD) three times per evaluation for want of uniform
+        // registers -- 12 issue slots against one move.
+        int soff = s * kRowsPad;
+#if PB_SMEM_VECTOR_ADDR
+        asm volatile("" : "+r"(soff));
+#endif
+        const SmemConsts<CLS> k = {s_pf + soff};
         ResNodes nodes = {nullptr, 0, 0, 0};
         if (kResonant) {
             const int4 rn = s_res[s];

@@ -110,7 +110,12 @@ int main(int argc, char **argv) {
     for (std::size_t i = 0; i < n; ++i) {
         l1[i].assign(&b1[i * PERTURB_SYNTH_LINE_STRIDE], 69);
         l2[i].assign(&b2[i * PERTURB_SYNTH_LINE_STRIDE], 69);
-        sats.push_back(Satellite::from_tle(l1[i], l2[i]));  // the reference
+        // the reference: Satellite::from_tle(std::string &, std::string &) hands &line[0] to
+        // twoline2rv, which EDITS the text in place (moves the sign of ndot / bstar one column to
+        // the left and writes the implied decimal points, src/sgp4.cpp twoline2rv): it gets its own
+        // copies, the batch below reads the pristine lines
+        std::string c1 = l1[i], c2 = l2[i];
+        sats.push_back(Satellite::from_tle(c1, c2));
     }
     SatelliteBatch batch = SatelliteBatch::from_tles(l1.data(), l2.data(), n, GravModel::WGS72, device);
     if (!batch.ok()) {
