@@ -312,6 +312,11 @@ sgp4_prop_kernel(const PropParams p) {
     __shared__ int s_perm[SATS];
     constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
     __shared__ int4 s_res[kResonant ? SATS : 1];  // {k0, count, first record, -}
+    // deep space: sin / cos of the per-time and per-satellite parts of the solar and lunar mean
+    // anomalies (ThirdBodyPhase, sgp4_eval.cuh): [0, N) Sun, [N, 2N) Moon
+    constexpr bool kDeepCls = (CLS >= PB_CLS_DEEP_NR);
+    __shared__ __align__(16) double2 s_tphase[kDeepCls ? 2 * kTimeTile : 1];
+    __shared__ __align__(16) double2 s_sphase[kDeepCls ? 2 * SATS : 1];
 
     const int ttile = blockIdx.x % p.n_time_tiles;
     const int stile_sub = blockIdx.x / p.n_time_tiles;
@@ -343,8 +348,20 @@ sgp4_prop_kernel(const PropParams p) {
         // Lanes past the end of the grid re-evaluate the last time (never stored): a made-up
         // time such as 0 would be ~1e9 minutes from epoch and spin the resonance integrator.
         const int k = min(k_base + i, p.m - 1);
-        s_ta[i] = p.ta[k];
-        s_tb[i] = p.use_jd ? p.tb[k] : 0.0;
+        const double ta_k = p.ta[k], tb_k = p.use_jd ? p.tb[k] : 0.0;
+        s_ta[i] = ta_k;
+        s_tb[i] = tb_k;
+        if (kDeepCls) {
+            phase_of_time(phase_minutes_of_time(p.use_jd, ta_k, tb_k), s_tphase[i],
+                          s_tphase[kTimeTile + i]);
+        }
+    }
+    if (kDeepCls && threadIdx.x < SATS) {  // (a CTA has at least 32 threads)
+        const double *f = p.pf + sat0 + threadIdx.x;
+        phase_of_satellite(f[static_cast<size_t>(PF_ZMOS) * p.n_pad], f[static_cast<size_t>(PF_ZMOL) * p.n_pad],
+                           phase_minutes_of_epoch(p.use_jd, f[static_cast<size_t>(PF_JD0) * p.n_pad],
+                                                  f[static_cast<size_t>(PF_JDF0) * p.n_pad]),
+                           s_sphase[threadIdx.x], s_sphase[SATS + threadIdx.x]);
     }
     __syncthreads();
 
@@ -418,8 +435,14 @@ sgp4_prop_kernel(const PropParams p) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const double t = tsince_of(p.use_jd, ta[j], tb[j], k(PF_JD0), k(PF_JDF0));
+                ThirdBodyPhase ph;
+                if (kDeepCls) {
+                    ph = phase_combine(s_sphase[s], s_sphase[SATS + s], s_tphase[i0 + j],
+                                       s_tphase[kTimeTile + i0 + j]);
+                }
                 cd[j] = sgp4_eval<CLS, false, true>(k, p.g, p.opsmode_a != 0, no_flags, t, r[j],
-                                                    nullptr, kResonant ? &nodes : nullptr);
+                                                    nullptr, kResonant ? &nodes : nullptr,
+                                                    kDeepCls ? &ph : nullptr);
             }
             const int kt = k_base + i0;
             const bool w0 = (cd[0] == 0) || (cd[0] == 6), w1 = (cd[1] == 0) || (cd[1] == 6);
@@ -458,9 +481,14 @@ sgp4_prop_kernel(const PropParams p) {
                                        k(PF_JD0), k(PF_JDF0));
             double r[6];
             Sgp4Side side;
+            ThirdBodyPhase ph;
+            if (kDeepCls) {
+                ph = phase_combine(s_sphase[s], s_sphase[SATS + s], s_tphase[i0 + kTimeStep * j],
+                                   s_tphase[kTimeTile + i0 + kTimeStep * j]);
+            }
             const int cd = sgp4_eval<CLS, WANT_ELEMENTS, true>(
                 k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
-                kResonant ? &nodes : nullptr);
+                kResonant ? &nodes : nullptr, kDeepCls ? &ph : nullptr);
             const int kt = k_base + i0 + kTimeStep * j;
             // every lane of the warp is here (uniform control flow): one vote decides whether
             // the stores need the NaN selects at all
@@ -643,6 +671,18 @@ __global__ void __launch_bounds__(kThreads)
 sgp4_prop_short_kernel(const PropParams p, int tile_count) {
     constexpr bool WANT_ELEMENTS = (MODE == kModeElements);
     constexpr bool kResonant = (CLS == PB_CLS_DEEP_R1 || CLS == PB_CLS_DEEP_R2);
+    constexpr bool kDeepCls = (CLS >= PB_CLS_DEEP_NR);
+    // the same per-time / per-satellite split of the solar and lunar mean anomalies as the
+    // long-grid kernel (same functions on the same inputs: same bits)
+    __shared__ __align__(16) double2 s_tphase[kDeepCls ? 2 * kShortGrid : 1];
+    if (kDeepCls) {
+        if (static_cast<int>(threadIdx.x) < p.m) {
+            const int kt = threadIdx.x;
+            phase_of_time(phase_minutes_of_time(p.use_jd, p.ta[kt], p.use_jd ? p.tb[kt] : 0.0),
+                          s_tphase[kt], s_tphase[kShortGrid + kt]);
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (warp_all(tile >= tile_count)) return;
@@ -663,6 +703,11 @@ sgp4_prop_short_kernel(const PropParams p, int tile_count) {
     const ClassFlags no_flags = {false, false, 0};
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     const double jd0 = k(PF_JD0), jdf0 = k(PF_JDF0);
+    double2 sat_sun = make_double2(0.0, 1.0), sat_moon = make_double2(0.0, 1.0);
+    if (kDeepCls) {
+        phase_of_satellite(k(PF_ZMOS), k(PF_ZMOL), phase_minutes_of_epoch(p.use_jd, jd0, jdf0),
+                           sat_sun, sat_moon);
+    }
     LaneSummary acc = {__longlong_as_double(0x7ff0000000000000LL),
                        __longlong_as_double(0xfff0000000000000LL), -1, -1, 0, -1, 0};
 #pragma unroll 1
@@ -671,9 +716,11 @@ sgp4_prop_short_kernel(const PropParams p, int tile_count) {
         const double t = tsince_of(p.use_jd, ta, tb, jd0, jdf0);
         double r[6];
         Sgp4Side side;
+        ThirdBodyPhase ph;
+        if (kDeepCls) ph = phase_combine(sat_sun, sat_moon, s_tphase[kt], s_tphase[kShortGrid + kt]);
         const int cd = sgp4_eval<CLS, WANT_ELEMENTS, true>(
             k, p.g, p.opsmode_a != 0, no_flags, t, r, WANT_ELEMENTS ? &side : nullptr,
-            (kResonant && nodes.table != nullptr) ? &nodes : nullptr);
+            (kResonant && nodes.table != nullptr) ? &nodes : nullptr, kDeepCls ? &ph : nullptr);
         if (dst < 0) continue;
         const bool written = (cd == 0) || (cd == 6);
         if (MODE == kModeSummary) {

@@ -662,18 +662,35 @@ def _mixed_batch(n=3000, seed=5):
 
 
 def test_jd_and_minutes_entry_points_agree():
+    """Satellite::propagate(jd) IS propagate_from_epoch((jd - epoch) * 1440) in the reference
+    (perturb.cpp:236-242). Near-Earth satellites: the two entry points give the same bits. Deep
+    space: kernel 2 splits the solar / lunar mean anomalies into a per-satellite and a per-time
+    part (ThirdBodyPhase, sgp4_eval.cuh), and the two entry points split at different reference
+    points -- a few 1e-13 rad in angles whose terms move the state by kilometres at most."""
     L1, L2 = _mixed_batch(1000)
     b = pb.SatelliteBatch.from_tles(L1, L2)
     jd0, fr0 = b.epoch()
-    # all satellites share one epoch here so that one mins grid equals one jd grid
-    L1 = [L1[0]] * 64
-    L2 = [L2[0]] * 64
-    b = pb.SatelliteBatch.from_tles(L1, L2)
+    cls = b.orbit_class()
     jd, fr = pb.synth_time_grid(300)
-    mins = ((jd - jd0[0]) + (fr - fr0[0])) * 1440.0  # perturb.cpp:80-83, 237-238
-    pa, ea = b.propagate(jd, fr)
-    pb_, eb = b.propagate_from_epoch(mins)
-    assert np.array_equal(ea, eb) and np.array_equal(pa, pb_, equal_nan=True)
+    seen = set()
+    for i in range(1000):
+        if cls[i] in seen:
+            continue
+        seen.add(int(cls[i]))
+        # all satellites share one epoch here so that one mins grid equals one jd grid
+        one = pb.SatelliteBatch.from_tles([L1[i]] * 64, [L2[i]] * 64)
+        mins = ((jd - jd0[i]) + (fr - fr0[i])) * 1440.0  # perturb.cpp:80-83, 237-238
+        pa, ea = one.propagate(jd, fr)
+        pb_, eb = one.propagate_from_epoch(mins)
+        assert np.array_equal(ea, eb), cls[i]
+        if cls[i] <= 1:
+            assert np.array_equal(pa, pb_, equal_nan=True), cls[i]
+        else:
+            ok = np.isin(ea, (0, 6))
+            assert ok.any() and np.array_equal(np.isnan(pa), np.isnan(pb_))
+            assert np.abs(pa - pb_)[0:3][:, ok].max() < 1e-9, cls[i]
+            assert np.abs(pa - pb_)[3:6][:, ok].max() < 1e-12, cls[i]
+    assert seen == {0, 1, 2, 3, 4}
 
 
 def test_time_chunking_and_strided_output_are_bit_invariant():
