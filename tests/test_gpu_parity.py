@@ -693,6 +693,52 @@ def test_jd_and_minutes_entry_points_agree():
     assert seen == {0, 1, 2, 3, 4}
 
 
+def test_rotated_argument_of_latitude_and_its_general_route():
+    """Near-Earth full-drag class: sin/cos(u) comes from rotations of sin/cos(xmdf) and
+    sin/cos(argpp) by the small angle eps = drag corrections of M + long-period term while
+    |eps| < 2^-4, and from the general route (u reduced, Newton / general sin/cos) beyond that
+    or for e^2 >= 4e-4 (sgp4_eval.cuh, Kepler section). Both populations must be present here
+    -- eps is recomputed from the oracle's record -- and both must meet the bar; the choice is
+    per lane, so the same times inside another grid give the same bits."""
+    n = 3000
+    b1, b2 = pb.synth_catalog(2, n, seed=21)
+    L1, L2 = pb.block_to_lines(b1, n), pb.block_to_lines(b2, n)
+    b = pb.SatelliteBatch.from_tles(L1, L2)
+    orc = port.OracleSatellites.from_tle_lines(L1, L2, 1, "i", flavor=1)
+    mins = np.concatenate([np.linspace(-2880.0, 10080.0, 37), np.linspace(12000.0, 90000.0, 27)])
+    f = {k: np.asarray(orc.field(k)) for k in ("no_unkozai", "t2cof", "t3cof", "t4cof", "t5cof",
+                                                "omgcof", "xmcof", "eta", "delmo", "isimp", "ecco")}
+    t = mins[None, :]
+    templ = f["t2cof"][:, None] * t**2 + f["t3cof"][:, None] * t**3 + t**4 * (
+        f["t4cof"][:, None] + t * f["t5cof"][:, None])
+    # bound of |delomg + delm| + |no * templ|: the angle the device rotates by (the long-period
+    # term adds ~1e-6)
+    eps = np.abs(f["omgcof"][:, None] * t) + np.abs(f["xmcof"][:, None]) * (
+        (1.0 + np.abs(f["eta"][:, None]))**3 + np.abs(f["delmo"][:, None])) + np.abs(
+        f["no_unkozai"][:, None] * templ)
+    eo, ro, vo, _ = orc.propagate_grid(mins, None, use_jd=False, nthreads=8)
+    full_drag = (b.orbit_class() == 0)[:, None] & (eo == 0)
+    circular = (f["ecco"] < 0.015)[:, None]
+    rotated = full_drag & circular & (eps < 0.03)
+    general = full_drag & (eps > 0.2)
+    assert rotated.sum() > 50000 and general.sum() > 5000, (rotated.sum(), general.sum())
+    pv, err = b.propagate_from_epoch(mins)
+    pos, vel = np.moveaxis(pv[0:3], 0, -1), np.moveaxis(pv[3:6], 0, -1)
+    sr, sv = oracle_sensitivity_mins(orc, mins)
+    stats = compare_states(err, pos, vel, eo, ro, vo, sr, sv, what="rotated u",
+                           horizon_min=mins[None, :])
+    assert stats["max_ratio_widened"] < 1.0
+    d = np.abs(pos - ro).max(-1)
+    week = (np.abs(mins) <= 10080.0)[None, :]
+    cond = (SENS_GAIN * sr <= 1e-6)
+    assert d[rotated & week & cond].max() < 1e-7  # (the general route meets the scaled bar above)
+    # a sub-grid (other warps, other tiles, the short-grid kernel) reproduces the bits
+    sel = np.array([3, 17, 36, 40, 55, 63])
+    pv_s, err_s = b.propagate_from_epoch(mins[sel].copy())
+    assert np.array_equal(err_s, err[:, sel])
+    assert np.array_equal(pv_s, pv[:, :, sel], equal_nan=True)
+
+
 def test_time_chunking_and_strided_output_are_bit_invariant():
     L1, L2 = _mixed_batch(2000)
     b = pb.SatelliteBatch.from_tles(L1, L2)
