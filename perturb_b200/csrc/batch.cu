@@ -601,7 +601,9 @@ int peer_ready(perturb_gpu_batch *b, int owner) {
 
 int ensure_workers(perturb_gpu_batch *b) {
     if (b->workers != nullptr) return PERTURB_GPU_OK;
-    unsigned threads = pb::default_host_workers();
+    int devices = 1;
+    if (cudaGetDeviceCount(&devices) != cudaSuccess) devices = 1;
+    unsigned threads = pb::default_host_workers(devices);
     if (const char *e = std::getenv("PERTURB_GPU_HOST_THREADS")) {
         const int v = std::atoi(e);
         if (v >= 1 && v <= 256) threads = static_cast<unsigned>(v);

@@ -2,13 +2,23 @@
 #include "host_workers.h"
 
 #include <algorithm>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 namespace pb {
 
-unsigned default_host_workers() {
+unsigned default_host_workers(int visible_devices) {
     unsigned hw = std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) {
+        hw = static_cast<unsigned>(CPU_COUNT(&set));  // taskset / cgroup limits count
+    }
+#endif
     if (hw == 0) hw = 2;
-    return std::min(16u, std::max(1u, hw / 2));
+    const unsigned pools = static_cast<unsigned>(std::max(1, visible_devices));
+    return std::min(16u, std::max(2u, hw / (2 * pools)));
 }
 
 HostWorkers::HostWorkers(unsigned threads)

@@ -42,9 +42,12 @@ private:
     bool stop_;
 };
 
-// Default pool size for a machine: half the hardware threads, at least 1, at most 16 (the
-// scatter is memory bound: more threads only fight over the memory controllers).
-unsigned default_host_workers();
+// Default pool size of ONE handle: half the CPUs this process may run on, shared between as many
+// handles as the box has GPUs (one process per GPU, or one process with a handle per GPU: either
+// way that many pools scatter at once, and on 8 GPUs each handle's share of the link is an
+// eighth); at least 2, at most 16 (the scatter is memory bound: more threads only fight over the
+// memory controllers).
+unsigned default_host_workers(int visible_devices);
 
 }  // namespace pb
 
