@@ -2,6 +2,7 @@
 """Benchmark of the hot path: batched SGP4 `Satellite::propagate` on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2]
+                    [--quick | --e2e-only | --no-extra]
 
 A "step" is one pass of the hot path over one batch: every satellite of the rank's catalogue
 shard propagated to every time of the grid (BASELINE.json configs[1]: 30 000 near-Earth

@@ -2,7 +2,8 @@
 // over Satellite::propagate(JulianDate, StateVector&) (src/perturb.cpp:236-242).
 //
 // Work decomposition:
-//   * a CTA owns one tile of 32 class-sorted satellites x one tile of the time grid;
+//   * a CTA owns 32, 16 or 8 satellites of one tile of 32 class-sorted satellites x one tile of
+//     the time grid (fewer satellites per CTA on launches of few waves: shorter last wave);
 //   * the tile's per-satellite constants are read coalesced from the field-major layout
 //     (32 consecutive satellites = one 256 B row per field) and staged in shared memory,
 //     and so is the CTA's slice of the time grid;
