@@ -842,20 +842,23 @@ int propagate_impl(perturb_gpu_batch *b, const double *ta, const double *tb, boo
     const size_t bytes_per_eval = dpe * sizeof(double) + sizeof(int32_t);
     size_t budget = std::min<size_t>(free_b / 4, static_cast<size_t>(8) << 30);  // per buffer
     for (int i = 0; i < 2; ++i) budget = std::max(budget, b->stage_cap[i] * bytes_per_eval);
-    // The copy takes ~40x as long as the kernel (PCIe 55 GB/s against 2 TB/s of output): at least
-    // four chunks, so that all but the first kernel hides behind a copy; bounce chunks of
-    // ~128 MiB, whole time tiles of kernel 2 where that is possible.
+    // Pinned destinations: ONE chunk by default, i.e. the kernel (2 % of the step: PCIe 55 GB/s
+    // against 2.5 TB/s of output) followed by one linear copy per buffer. Time-chunks would hide
+    // the kernel behind the previous chunk's copy, but their copies are 2-D (row segments of the
+    // caller's [n][m] planes) and those run at 39-50 GB/s on these boxes where the linear copy
+    // reaches 54 of the raw 57 (profiles/r2n_e2e_chunks_*.jsonl; PERTURB_GPU_HOST_CHUNKS overrides,
+    // and grids whose staging does not fit the budget are chunked anyway).
     const size_t total_bytes = bytes_per_eval * b->n * m;
     if (direct && total_bytes > (static_cast<size_t>(256) << 20)) {
-        // two chunks by default: the second kernel hides behind the first copy and the row
-        // segments of the 2-D copies stay long (PERTURB_GPU_HOST_CHUNKS overrides: tuning)
-        size_t want = 2;
+        size_t want = 1;
         if (const char *e = std::getenv("PERTURB_GPU_HOST_CHUNKS")) {
             const int v = std::atoi(e);
             if (v >= 1 && v <= 64) want = static_cast<size_t>(v);
         }
-        budget = std::min(budget, std::max<size_t>((total_bytes + want - 1) / want + bytes_per_eval * b->n * 2,
-                                                   static_cast<size_t>(16) << 20));
+        if (want > 1) {
+            budget = std::min(budget, std::max<size_t>((total_bytes + want - 1) / want + bytes_per_eval * b->n * 2,
+                                                       static_cast<size_t>(16) << 20));
+        }
     }
     if (!direct) budget = std::min(budget, static_cast<size_t>(128) << 20);
     const size_t m_even = (m + 1) & ~static_cast<size_t>(1);
