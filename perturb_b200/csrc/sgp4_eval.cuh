@@ -219,15 +219,12 @@ __device__ __forceinline__ void resonance_advance(double xndt, double xldot, dou
 // remainder |t| - 720 n (exactly representable) so that the count is the reference's.
 __device__ __forceinline__ int resonance_step_count(double t) {
     const double at = fabs(t);
-    if (!(at < 1.0e9)) return 0;  // non-finite or absurd time: garbage in, no spinning
-    int n = static_cast<int>(at * (1.0 / 720.0));
+    // (selects throughout: as branches this was a reconvergence region per evaluation)
+    const bool sane = at < 1.0e9;  // non-finite or absurd time: garbage in, no spinning
+    int n = static_cast<int>((sane ? at : 0.0) * (1.0 / 720.0));
     const double rem = __fma_rn(-720.0, static_cast<double>(n), at);
-    if (rem >= 720.0) {
-        ++n;
-    } else if (rem < 0.0) {
-        --n;
-    }
-    return n;
+    n += (rem >= 720.0) ? 1 : ((rem < 0.0) ? -1 : 0);
+    return sane ? n : 0;
 }
 
 // Integrator nodes tabulated per satellite by the pre-pass kernel: record j holds the state
@@ -753,10 +750,10 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         }
         PB_FAIL_IF(ep < 0.0 || ep > 1.0, 3);  // :1938
         aycof = -0.5 * g.j3oj2 * sinip;
-        if (fabs(cosip + 1.0) > kMc[MC_1P5EM12]) {
-            xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), 1.0 + cosip);
-        } else {
-            xlcof = -0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip) / 1.5e-12;
+        {   // :1954-1957: the denominator is 1 + cos(i), or 1.5e-12 within that of a retrograde
+            // equatorial orbit -- a select, not a branch
+            const double den = (fabs(cosip + 1.0) > kMc[MC_1P5EM12]) ? 1.0 + cosip : kMc[MC_1P5EM12];
+            xlcof = div_fast(-0.25 * g.j3oj2 * sinip * (3.0 + 5.0 * cosip), den);
         }
         if (WANT_SIDE && code == 0) {
             side->aycof = aycof;

@@ -191,13 +191,13 @@ __device__ __forceinline__ double sqrt_fast(double x) {
 __device__ __forceinline__ double fmod_2pi(double x) {
     const double q = __dadd_rn(__fma_rn(x, kMc[MC_INV_TWOPI], kRintMagic),
                                -kRintMagic);
-    double r = __fma_rn(-q, kMc[MC_TWOPI], x);
-    if (x >= 0.0) {
-        if (r < 0.0) r = __dadd_rn(r, kMc[MC_TWOPI]);
-    } else {
-        if (r > 0.0) r = __dadd_rn(r, -kMc[MC_TWOPI]);
-    }
-    return r;
+    const double r = __fma_rn(-q, kMc[MC_TWOPI], x);
+    // one add of +2pi, -2pi or 0 chosen by selects: as nested branches this was two
+    // reconvergence regions per call on the warp-uniform path
+    const bool up = (x >= 0.0) && (r < 0.0);
+    const bool down = !(x >= 0.0) && (r > 0.0);
+    const double fix = up ? kMc[MC_TWOPI] : (down ? -kMc[MC_TWOPI] : 0.0);
+    return __dadd_rn(r, fix);
 }
 
 // Same reduction modulo the DOUBLE 2pi without the sign fix-up: result in [-pi, pi]. For
