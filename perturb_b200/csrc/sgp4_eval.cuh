@@ -18,7 +18,15 @@
 //     multiply, atan2 + sincos of the argument of latitude by a rotation of the (unit) vector
 //     (sinu, cosu), sqrt(pl) by sqrt(am) sqrt(1 - el2), and sin/cos of angles that differ from
 //     an angle with known sin/cos by a small amount (drag correction of M, the solar / lunar
-//     equation of centre in dpper, the perturbed inclination) by short Taylor rotations.
+//     equation of centre in dpper, the perturbed inclination) by short Taylor rotations;
+//   * Kepler's equation: closed form for nearly circular orbits, Halley's iteration for
+//     e^2 < 0.64, the reference's Newton loop for the rest (kepler_small, kepler_halley,
+//     kepler_newton): all land on the root the reference's loop converges to;
+//   * near-Earth full-drag class: sin/cos of the argument of latitude by rotating sin/cos(xmdf)
+//     through argpp and the small drag / long-period angle, without the reference's three
+//     fmod reductions (kRotU in sgp4_eval);
+//   * deep space: sin/cos of the solar / lunar mean anomalies from a per-satellite and a
+//     per-time part that kernel 2 evaluates once per CTA (ThirdBodyPhase).
 // The record fields the reference overwrites on every call (t, error, am..nm, and for deep
 // space aycof/xlcof/con41/x1mth2/x7thm1) are returned through `Sgp4Side` when asked for.
 #ifndef PERTURB_B200_SGP4_EVAL_CUH
