@@ -22,6 +22,8 @@ Prints ONE JSON line (rank 0). Keys beyond the base contract:
                 std::vector<StateVector> (tests/cpp/dropin_bench.cpp, a C++ program).
   workloads     BASELINE.json configs 3, 4, 5 at full size (device-resident), each with its own
                 clocks and FP64-pipe share; c5_strong at N > 1 (1 M satellites / N per GPU).
+  e2e_rate_balanced  (N > 1) the e2e arm with satellite ranges proportional to each rank's
+                measured D2H rate (the GPUs of a box do not share the host links evenly).
   inproc_sharded  (N > 1, rank 0) one process driving all N GPUs: ShardedSatelliteBatch,
                 bit-identity against the unsharded batch, device-resident gather over NVLink.
 """
@@ -522,13 +524,67 @@ def d2h_ceiling(pb, torch, world, local, dev, dist, window_s=1.0):
         dist.all_reduce(t)
         total = float(t.item())
     del d, h
-    return {"d2h_ceiling_gbs": total,
+    return {"_own_gbs": own,
+            "d2h_ceiling_gbs": total,
             "d2h_ceiling_gbs_slowest_gpu": slowest,
             "d2h_ceiling_gbs_equal_shards": slowest * world,
             "d2h_ceiling_how": "all %d ranks at once, after a barrier: 256 MiB cudaMemcpyAsync pieces "
                                "device -> pinned host back to back for %.1f s each; bytes landed in the "
                                "common window, summed over ranks; equal_shards = N x the slowest rank "
                                "(equal satellite shards finish with the slowest GPU)" % (world, window_s)}
+
+
+def e2e_rate_balanced(pb, torch, workload, rank, world, local, dev, dist, steps, own_rate):
+    """(N > 1) The pinned-host arm once more over the SAME global catalogue (N x 30 000
+    satellites), split into contiguous satellite ranges proportional to the D2H rate each rank
+    measured while all ranks were copying (d2h_ceiling): the GPUs of a box do not share the host
+    links evenly (e.g. three behind one bridge, one alone), and with equal ranges the whole job
+    waits for the slowest. Same calls, same bytes in total; reported BESIDE `e2e` (equal ranges),
+    not instead of it."""
+    cfg, n, m = WORKLOADS[workload]
+    total = n * world
+    me = min(m, E2E_MAX_TIMES)
+    rates = [None] * world
+    dist.all_gather_object(rates, float(own_rate))
+    share = np.maximum(np.asarray(rates, dtype=np.float64), 1e-3)
+    cuts = np.round(np.concatenate([[0.0], np.cumsum(share / share.sum())]) * total).astype(np.int64)
+    cuts[-1] = total
+    for r in range(1, world):  # every rank keeps at least one tile of satellites
+        cuts[r] = min(max(cuts[r], cuts[r - 1] + 32), total - 32 * (world - r))
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    k = hi - lo
+    b1, b2 = pb.synth_catalog(cfg, total)
+    stride = pb.capi.SYNTH_LINE_STRIDE
+    batch = pb.SatelliteBatch.from_text(b1[lo * stride: hi * stride], b2[lo * stride: hi * stride],
+                                        pb.WGS72, "i", device=local, n=k)
+    jd, fr = pb.synth_time_grid(m)
+    h_jd = torch.tensor(jd[:me]).pin_memory()
+    h_fr = torch.tensor(fr[:me]).pin_memory()
+    h_out = torch.empty((6, k, me), dtype=torch.float64).pin_memory()
+    h_err = torch.empty((k, me), dtype=torch.int32).pin_memory()
+    batch.propagate(h_jd, h_fr, h_out, h_err)  # warm-up: staging buffers
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        batch.propagate(h_jd, h_fr, h_out, h_err)
+        _ = int(h_err[0, 0])
+    secs = pb.max_over_ranks(time.perf_counter() - t0, dist, dev)
+    ok = float((h_err == 0).double().mean())
+    batch.close()
+    del h_out, h_err
+    return {
+        "value": float(total) * me * steps / secs, "unit": "evals/s",
+        "what": "the e2e arm over the same global catalogue with satellite ranges proportional to "
+                "each rank's measured D2H rate (the job no longer waits for the GPUs behind the "
+                "busiest host bridge)",
+        "satellites_per_rank": [int(cuts[r + 1] - cuts[r]) for r in range(world)],
+        "d2h_rate_per_rank_gbs": [float(x) for x in rates],
+        "h2d_bytes_per_step": int(2 * me * 8) * world,
+        "d2h_bytes_per_step": int(float(total) * me * 52),
+        "d2h_gbs": float(total) * me * steps * BYTES_PER_EVAL / secs * 1e-9,
+        "times_per_step": me, "steps": steps, "ok_fraction_this_rank": ok,
+    }
 
 
 def add_ceiling_fractions(e2e):
@@ -604,7 +660,11 @@ def run_gpu(args):
     codes_ok = e2e.pop("ok_fraction")
     if args.e2e_only:
         e2e.update(d2h_ceiling(pb, torch, world, local, dev, dist))
+        own_rate = e2e.pop("_own_gbs")
         add_ceiling_fractions(e2e)
+        if world > 1:
+            e2e["rate_balanced"] = e2e_rate_balanced(pb, torch, args.workload, rank, world, local,
+                                                     dev, dist, e2e_steps, own_rate)
         per_rank = [None] * world
         if dist is not None:
             dist.all_gather_object(per_rank, e2e["d2h_gbs_this_rank"])
@@ -633,6 +693,11 @@ def run_gpu(args):
     rec_value = float(n) * me * world * e2e_steps / rec_s
     del h_states, h_err
     ceiling = d2h_ceiling(pb, torch, world, local, dev, dist)
+    own_rate = ceiling.pop("_own_gbs")
+    balanced = None
+    if world > 1 and not args.no_extra:
+        balanced = e2e_rate_balanced(pb, torch, args.workload, rank, world, local, dev, dist,
+                                     e2e_steps, own_rate)
     # ---- the fused consumer (N3): host time grid in, one 40-byte summary per satellite out ----
     hs_jd = torch.tensor(jd).pin_memory()
     hs_fr = torch.tensor(fr).pin_memory()
@@ -827,6 +892,7 @@ def run_gpu(args):
             "steps": e2e_steps,
         },
         "e2e_dropin": dropin,
+        "e2e_rate_balanced": balanced,
         "e2e_summary": {
             "value": sum_value,
             "unit": "evals/s",
