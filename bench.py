@@ -546,12 +546,8 @@ def e2e_rate_balanced(pb, torch, workload, rank, world, local, dev, dist, steps,
     me = min(m, E2E_MAX_TIMES)
     rates = [None] * world
     dist.all_gather_object(rates, float(own_rate))
-    share = np.maximum(np.asarray(rates, dtype=np.float64), 1e-3)
-    cuts = np.round(np.concatenate([[0.0], np.cumsum(share / share.sum())]) * total).astype(np.int64)
-    cuts[-1] = total
-    for r in range(1, world):  # every rank keeps at least one tile of satellites
-        cuts[r] = min(max(cuts[r], cuts[r - 1] + 32), total - 32 * (world - r))
-    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    ranges = pb.rate_ranges(total, rates)
+    lo, hi = ranges[rank]
     k = hi - lo
     b1, b2 = pb.synth_catalog(cfg, total)
     stride = pb.capi.SYNTH_LINE_STRIDE
@@ -578,7 +574,7 @@ def e2e_rate_balanced(pb, torch, workload, rank, world, local, dev, dist, steps,
         "what": "the e2e arm over the same global catalogue with satellite ranges proportional to "
                 "each rank's measured D2H rate (the job no longer waits for the GPUs behind the "
                 "busiest host bridge)",
-        "satellites_per_rank": [int(cuts[r + 1] - cuts[r]) for r in range(world)],
+        "satellites_per_rank": [b - a for a, b in ranges],
         "d2h_rate_per_rank_gbs": [float(x) for x in rates],
         "h2d_bytes_per_step": int(2 * me * 8) * world,
         "d2h_bytes_per_step": int(float(total) * me * 52),

@@ -6,7 +6,8 @@ from .batch import (  # noqa: F401
     COE_NAMES, SatelliteBatch, block_to_lines, classical_elements, parse_tle_blocks, parse_tles, synth_catalog,
     synth_time_grid)
 from .sharding import (  # noqa: F401
-    ShardedSatelliteBatch, estimate_class, max_over_ranks, plan_ranges, shard_blocks, shard_range)
+    ShardedSatelliteBatch, estimate_class, max_over_ranks, plan_ranges, rate_ranges, shard_blocks,
+    shard_range)
 from .capi import WGS72, WGS72_OLD, WGS84, PerturbGpuError  # noqa: F401
 
 SGP4_ERROR_NAMES = (

@@ -77,6 +77,23 @@ def plan_ranges(costs, nshards):
     return [(cuts[i], cuts[i + 1]) for i in range(nshards)]
 
 
+def rate_ranges(n, rates, min_count=32):
+    """Contiguous ranges [(lo, hi)] whose satellite COUNTS are proportional to `rates` (e.g. the
+    D2H rate each GPU of a box reaches while all of them copy: host-gathered output is bound by
+    the links, not by the kernels, and the GPUs of a box do not always share them evenly). Every
+    range keeps at least `min_count` satellites (one tile) while n allows it."""
+    rates = np.maximum(np.asarray(rates, dtype=np.float64), 1e-9)
+    k = rates.size
+    if k < 1:
+        raise ValueError("rates must name at least one shard")
+    min_count = min(int(min_count), n // k)
+    cuts = np.round(np.concatenate([[0.0], np.cumsum(rates / rates.sum())]) * n).astype(np.int64)
+    cuts[0], cuts[-1] = 0, n
+    for r in range(1, k):
+        cuts[r] = min(max(cuts[r], cuts[r - 1] + min_count), n - min_count * (k - r))
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(k)]
+
+
 def max_over_ranks(value, dist=None, device=None):
     """MAX-reduce a per-rank timing; identity without a process group."""
     if dist is None or not dist.is_initialized():

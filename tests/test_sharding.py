@@ -39,6 +39,25 @@ def test_estimate_class_matches_the_mix_of_each_config():
     assert counts[2] == 300 and counts[3] == 200 and counts[4] == 100  # MEO+GTO, GEO, Molniya
 
 
+def test_rate_ranges_are_proportional_contiguous_and_never_empty():
+    from perturb_b200 import rate_ranges
+    # the 8-GPU box of profiles/r2f_n8_e2e_nobind.json: four GPUs at 11.7 GB/s, four at 16.6
+    r = rate_ranges(240000, [11.7] * 4 + [16.6] * 4)
+    assert r[0][0] == 0 and r[-1][1] == 240000
+    assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    counts = np.array([hi - lo for lo, hi in r])
+    assert np.allclose(counts[:4], 240000 * 11.7 / (4 * 28.3), atol=1) and np.allclose(
+        counts[4:], 240000 * 16.6 / (4 * 28.3), atol=1)
+    assert rate_ranges(120000, [18.25] * 4) == [(i * 30000, (i + 1) * 30000) for i in range(4)]
+    # a dead link keeps one tile; tiny catalogues are still partitioned exactly
+    r = rate_ranges(1000, [0.0, 50.0, 50.0])
+    assert r[0] == (0, 32) and r[-1][1] == 1000 and all(hi > lo for lo, hi in r)
+    r = rate_ranges(5, [1.0, 1.0, 1.0])
+    assert r[0][0] == 0 and r[-1][1] == 5 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    with pytest.raises(ValueError):
+        rate_ranges(10, [])
+
+
 def test_plan_ranges_balances_cost_not_count():
     rng = np.random.default_rng(0)
     # first half cheap, second half twice as expensive: the second shard must be shorter
