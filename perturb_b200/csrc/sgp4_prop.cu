@@ -24,10 +24,10 @@ namespace pb {
 namespace {
 
 // Resident CTAs per SM the register allocation is capped for (measured on B200, sweeps in
-// profiles/): the near-Earth bodies need 64-70 registers and do best at 7 CTAs (28 warps/SM;
-// 8 is within 0.5 %), the deep-space bodies at 6 (80 registers: the non-resonant and 24 h
-// bodies fit, the 12 h-resonant one spills 60 bytes and is still 1.3 % faster than at 5 CTAs
-// with 96 registers; 7 CTAs is level).
+// profiles/): the near-Earth bodies need 64-72 registers and do best at 7 CTAs (28 warps/SM;
+// 6 and 8 are within 1.5 %), the deep-space bodies at 6 (80 registers: the non-resonant and 24 h
+// bodies fit, the 12 h-resonant one spills 92 bytes and is level with 5 CTAs at 96 registers
+// without spills, profiles/r2m_variants.jsonl).
 #ifndef PB_MIN_BLOCKS_NEAR
 #define PB_MIN_BLOCKS_NEAR 7
 #endif
