@@ -347,11 +347,15 @@ private:
 /// A propagate call enqueues on every device first and synchronises afterwards, so with
 /// pinned host buffers (`pinned_alloc`) all devices compute and copy into their slices of the
 /// caller's arrays concurrently. Indices are the caller's, exactly as for `SatelliteBatch`.
+/// `device_share` (optional, one number per device): the relative share of the cost each device
+/// should get instead of an equal one -- e.g. the device -> host copy rate each GPU reaches while
+/// all of them copy, when the results are gathered into host memory: that path is bound by the
+/// host links, which the GPUs of a box do not always share evenly.
 class ShardedSatelliteBatch {
 public:
     ShardedSatelliteBatch(
         const TwoLineElement *tles, std::size_t n, const int *devices, std::size_t n_devices,
-        GravModel grav_model = GravModel::WGS72
+        GravModel grav_model = GravModel::WGS72, const double *device_share = nullptr
     )
         : n_(n), status_(PERTURB_GPU_OK) {
         if (n_devices == 0) {
@@ -362,7 +366,7 @@ public:
         for (std::size_t i = 0; i < n; ++i) {
             cost[i] = estimated_cost(tles[i]);
         }
-        cuts_ = plan_ranges(cost, n_devices);
+        cuts_ = plan_ranges(cost, n_devices, device_share);
         for (std::size_t s = 0; s < n_devices; ++s) {
             shards_.emplace_back(
                 tles + cuts_[s], cuts_[s + 1] - cuts_[s], grav_model, devices[s]
@@ -378,7 +382,8 @@ public:
     /// to place the range boundaries, then every shard parses its own range on its device.
     static ShardedSatelliteBatch from_tles(
         const std::string *lines_1, const std::string *lines_2, std::size_t n, const int *devices,
-        std::size_t n_devices, GravModel grav_model = GravModel::WGS72
+        std::size_t n_devices, GravModel grav_model = GravModel::WGS72,
+        const double *device_share = nullptr
     ) {
         ShardedSatelliteBatch out;
         out.n_ = n;
@@ -399,7 +404,7 @@ public:
             }
             cost[i] = estimated_cost(t);
         }
-        out.cuts_ = plan_ranges(cost, n_devices);
+        out.cuts_ = plan_ranges(cost, n_devices, device_share);
         for (std::size_t s = 0; s < n_devices; ++s) {
             out.shards_.push_back(SatelliteBatch::from_tles(
                 lines_1 + out.cuts_[s], lines_2 + out.cuts_[s], out.cuts_[s + 1] - out.cuts_[s],
@@ -557,18 +562,28 @@ public:
     }
 
     /// Cut points (n_shards + 1 of them, first 0, last n) of the contiguous split whose summed
-    /// costs are as equal as a prefix split allows.
+    /// costs are as equal -- or, with `share`, as proportional to the shards' shares -- as a
+    /// prefix split allows.
     static std::vector<std::size_t> plan_ranges(
-        const std::vector<double> &cost, std::size_t n_shards
+        const std::vector<double> &cost, std::size_t n_shards, const double *share = nullptr
     ) {
         const std::size_t n = cost.size();
         std::vector<double> cum(n + 1, 0.0);
         for (std::size_t i = 0; i < n; ++i) {
             cum[i + 1] = cum[i] + cost[i];
         }
+        double share_total = 0.0, share_before = 0.0;
+        for (std::size_t s = 0; share != nullptr && s < n_shards; ++s) {
+            share_total += share[s] > 0.0 ? share[s] : 0.0;
+        }
         std::vector<std::size_t> cuts(1, 0);
         for (std::size_t s = 1; s < n_shards; ++s) {
-            const double target = cum[n] * static_cast<double>(s) / static_cast<double>(n_shards);
+            double fraction = static_cast<double>(s) / static_cast<double>(n_shards);
+            if (share_total > 0.0) {
+                share_before += share[s - 1] > 0.0 ? share[s - 1] : 0.0;
+                fraction = share_before / share_total;
+            }
+            const double target = cum[n] * fraction;
             std::size_t k = cuts.back();
             while (k < n && cum[k + 1] - target < target - cum[k]) {
                 ++k;  // stop at the prefix closest to the target

@@ -57,18 +57,27 @@ def estimate_class(tles):
     return out
 
 
-def plan_ranges(costs, nshards):
-    """Contiguous ranges [(lo, hi)] * nshards whose summed cost is as equal as a prefix split
-    allows (every satellite lands in exactly one range; empty ranges only if n < nshards)."""
+def plan_ranges(costs, nshards, shares=None):
+    """Contiguous ranges [(lo, hi)] * nshards whose summed cost is as equal -- or, with `shares`
+    (one non-negative number per shard), as proportional to them -- as a prefix split allows
+    (every satellite lands in exactly one range; empty ranges only if n < nshards or a share
+    is zero)."""
     costs = np.asarray(costs, dtype=np.float64)
     n = costs.size
     if nshards < 1:
         raise ValueError("nshards must be >= 1")
+    frac = np.arange(nshards + 1, dtype=np.float64) / nshards
+    if shares is not None:
+        sh = np.maximum(np.asarray(shares, dtype=np.float64), 0.0)
+        if sh.size != nshards:
+            raise ValueError("one share per shard")
+        if sh.sum() > 0.0:
+            frac = np.concatenate([[0.0], np.cumsum(sh) / sh.sum()])
     cum = np.concatenate([[0.0], np.cumsum(costs)])
     total = cum[-1]
     cuts = [0]
     for s in range(1, nshards):
-        target = total * s / nshards
+        target = total * frac[s]
         k = int(np.searchsorted(cum, target, side="left"))
         if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, n)] - target):
             k -= 1
@@ -111,10 +120,12 @@ class ShardedSatelliteBatch:
         self.batches, self.ranges, self.n = batches, ranges, n
 
     @classmethod
-    def from_parsed(cls, tles, devices, grav=capi.WGS72, opsmode="i"):
+    def from_parsed(cls, tles, devices, grav=capi.WGS72, opsmode="i", shares=None):
+        """`shares`: relative share of the cost per device instead of equal ones, e.g. each GPU's
+        device -> host copy rate when the results are gathered into host memory."""
         n = len(tles)
         cost = np.array(CLASS_COST)[estimate_class(tles)]
-        ranges = plan_ranges(cost, len(devices))
+        ranges = plan_ranges(cost, len(devices), shares)
         batches = []
         for dev, (lo, hi) in zip(devices, ranges):
             sub = (capi.Tle * (hi - lo))(*tles[lo:hi])
@@ -122,9 +133,9 @@ class ShardedSatelliteBatch:
         return cls(batches, ranges, n)
 
     @classmethod
-    def from_tles(cls, lines1, lines2, devices, grav=capi.WGS72, opsmode="i", flavor=1):
+    def from_tles(cls, lines1, lines2, devices, grav=capi.WGS72, opsmode="i", flavor=1, shares=None):
         tles, _ = parse_tles(lines1, lines2, flavor)
-        return cls.from_parsed(tles, devices, grav, opsmode)
+        return cls.from_parsed(tles, devices, grav, opsmode, shares)
 
     def last_error(self):
         return np.concatenate([b.last_error() for b in self.batches]) if self.n else np.zeros(0, np.int32)

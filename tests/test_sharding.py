@@ -39,6 +39,21 @@ def test_estimate_class_matches_the_mix_of_each_config():
     assert counts[2] == 300 and counts[3] == 200 and counts[4] == 100  # MEO+GTO, GEO, Molniya
 
 
+def test_plan_ranges_with_device_shares():
+    cost = np.ones(1000)
+    assert sharding.plan_ranges(cost, 4, [1, 1, 1, 1]) == sharding.plan_ranges(cost, 4)
+    r = sharding.plan_ranges(cost, 4, [20.0, 20.0, 20.0, 45.0])  # profiles/r2p_n4_e2e_nobind.json
+    assert [hi - lo for lo, hi in r] == [190, 191, 190, 429] and r[-1][1] == 1000
+    # shares weigh COST, not count: the deep-space half costs 1.8x per satellite
+    cost = np.concatenate([np.full(500, 1170.0), np.full(500, 2097.0)])
+    r = sharding.plan_ranges(cost, 2, [1.0, 3.0])
+    got = [cost[lo:hi].sum() for lo, hi in r]
+    assert abs(got[0] / sum(got) - 0.25) < 2e-3
+    assert sharding.plan_ranges(np.ones(10), 3, [0.0, 1.0, 1.0])[0] == (0, 0)
+    with pytest.raises(ValueError):
+        sharding.plan_ranges(np.ones(10), 3, [1.0, 1.0])
+
+
 def test_rate_ranges_are_proportional_contiguous_and_never_empty():
     from perturb_b200 import rate_ranges
     # the 8-GPU box of profiles/r2f_n8_e2e_nobind.json: four GPUs at 11.7 GB/s, four at 16.6
