@@ -627,31 +627,24 @@ __device__ __forceinline__ int sgp4_eval(const K &k, const GravConsts &g, bool o
         mm = mm + no * templ;
     }
     const double mm_raw = mm;  // xmdf + drag corrections, unreduced
-    double xlm = mm + argpm + nodem;
+    double xlm = mm + argpm + nodem;  // (only the WANT_SIDE path uses it)
 
-    if (deep || WANT_SIDE) {
-        // dpper multiplies nodep itself by cos(i) in the Lyddane branch (:341) and compares it
-        // against atan2 output (:352): the representative matters, keep C fmod semantics. The
-        // same holds when the mean elements are handed back to the record (Om, om, mm).
+    if (WANT_SIDE) {
+        // the mean elements are handed back to the record (Om, om, mm): the representatives
+        // matter, keep the reference's sequence with C fmod semantics (:1884-1887)
         nodem = fmod_2pi(nodem);
-        if (WANT_SIDE) {
-            argpm = fmod_2pi(argpm);
-            xlm = fmod_2pi(xlm);
-            mm = fmod_2pi(xlm - argpm - nodem);
-        } else {
-            // only nodem's representative reaches a result (dpper's Lyddane branch, above).
-            // argpm stays unreduced: it grows by ~0.5 rad a week, enters sums that are reduced
-            // again (the 2 pi multiples drop out exactly in wrap_pi) and sin/cos, which take
-            // any angle.
-            xlm = wrap_pi(xlm);
-            mm = wrap_pi(xlm - argpm - nodem);
-        }
+        argpm = fmod_2pi(argpm);
+        xlm = fmod_2pi(xlm);
+        mm = fmod_2pi(xlm - argpm - nodem);
     } else if (!kRotU) {
-        // near-Earth: nodem (~0.1 rad a week) and argpm (~0.5 rad a week) likewise stay
-        // unreduced; the fast angle, the mean anomaly, is reduced exactly where the reference
-        // reduces it (:1884-1887)
-        xlm = wrap_pi(xlm);
-        mm = wrap_pi(xlm - argpm - nodem);
+        // The reference reduces xlm and then mm = xlm - argpm - nodem: modulo 2 pi that IS mm,
+        // so ONE exact reduction of mm replaces two reductions and four sums at the magnitude of
+        // the unreduced angles (whose rounding, ~1e-13 rad, the reference's result carries).
+        // argpm (~0.5 rad a week) and nodem (~0.1 rad a week) stay unreduced: they enter sums
+        // that are reduced again and sin/cos, which take any angle. The one place where the
+        // node's representative reaches a result, dpper's Lyddane branch (it multiplies nodep
+        // by cos(i), :341), reduces it there with C fmod semantics.
+        mm = wrap_pi(mm);
     }  // kRotU: the mean anomaly only enters u, which is formed from mm_raw (Kepler section)
 
     if (WANT_SIDE && code == 0) {
