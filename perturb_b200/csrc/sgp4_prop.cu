@@ -404,10 +404,11 @@ sgp4_prop_kernel(const PropParams p) {
     for (int s = SPLIT ? sat_first : 0; s < SATS; s += SPLIT ? sat_step : 1) {
         const int dst = s_perm[s];
         if (dst < 0) continue;  // padding slot (warp-uniform)
-        // The satellite's block is addressed through a VECTOR register (the offset is made opaque
-        // to the uniformity analysis): kept uniform, ptxas re-forms the shared-window address
-        // (S2UR CgaCtaId, UMOV, ULEA, UIMAD) three times per evaluation for want of uniform
-        // registers -- 12 issue slots against one move.
+        // The block's offset is made opaque to the optimiser (an empty volatile asm): the
+        // compiler then forms the block's shared-window address once per satellite and keeps it in
+        // one uniform register across the evaluation; left to itself it re-formed it (S2UR
+        // CgaCtaId, UMOV, ULEA, UIMAD) three times per evaluation -- 12 issue slots (SASS of
+        // both forms compared with scripts/sass_path.py).
         int soff = s * kRowsPad;
 #if PB_SMEM_VECTOR_ADDR
         asm volatile("" : "+r"(soff));
